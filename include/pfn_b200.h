@@ -1,0 +1,143 @@
+/*
+ * pfn_b200.h — C ABI of libpfn_b200.so, the sm_100a kernel library behind the PFN training hot path
+ * (prior sample -> masked-attention transformer fwd+bwd -> BarDistribution NLL).
+ *
+ * The reference (automl/TransformersCanDoBayesianInference @ 9c20031) has no FFI of its own: its hot path is
+ * Python calling torch.nn / gpytorch.  Each entry point below names the reference call it replaces
+ * (file:line into the reference tree, or `torch:` for the library code the reference reaches).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers into caller-owned buffers (PyTorch CUDA tensors); nothing is allocated
+ *     or retained by the library; `stream` is a cudaStream_t passed as void*; no call synchronises.
+ *   - activations are sequence-first like the reference: token row = t*B + b, row-major [T*B, cols] with an
+ *     explicit leading dimension (elements).
+ *   - return 0 on success; non-zero on failure with a message in pfn_last_error() (thread-local).  No C++
+ *     exception crosses this boundary.
+ *   - dtype codes: PFN_F32 / PFN_BF16.  bf16 kernels accumulate and keep all statistics in fp32.
+ */
+#ifndef PFN_B200_H_
+#define PFN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PFN_B200_VERSION 1
+
+enum { PFN_F32 = 0, PFN_BF16 = 1 };
+enum { PFN_EPI_NONE = 0, PFN_EPI_GELU = 1, PFN_EPI_GELU_BWD = 2 };
+enum { PFN_KERNEL_RBF = 0, PFN_KERNEL_MATERN12 = 1, PFN_KERNEL_MATERN32 = 2, PFN_KERNEL_MATERN52 = 3 };
+
+const char* pfn_last_error(void);
+int pfn_version(void);
+int pfn_num_sms(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * GEMM:  C[M,N] (+)= epi( sum_k A(m,k) B(n,k) + bias[n] )  (+ aux[m,n] residual)
+ *   K-major operand : element (i,k) at base + i*ld + k;   MN-major operand : element (i,k) at base + k*ld + i
+ *   epilogue GELU      : C = gelu_erf(acc+bias), optional C2 = acc+bias (pre-activation, saved for backward)
+ *   epilogue GELU_BWD  : C = acc * gelu_erf'(aux)
+ *   accumulate / k_splits>1 : atomic fp32 accumulation into C (weight gradients)
+ * Replaces: nn.Linear / in_proj / out_proj / linear1 / linear2 / decoder GEMMs and their autograd backward
+ *   (reference transformer.py:17-18,23,84-85; torch:nn/functional.py:6478; torch:nn/modules/transformer.py:980-982).
+ * pfn_gemm_bf16_tc : tcgen05 + TMA + TMEM path (bf16 operands; lda/ldb multiples of 8; 16-byte aligned bases).
+ * pfn_gemm_simt    : fp32-FMA path for fp32 parity mode and shapes the tensor-core path does not take.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pfn_gemm_desc {
+  int M, N, K;
+  const void* A; int lda; int a_mn_major;
+  const void* B; int ldb; int b_mn_major;
+  void* C; int ldc; int c_dtype;
+  const float* bias;
+  const void* aux; int ld_aux;
+  void* C2; int ldc2;
+  int epilogue;
+  int accumulate;
+  int k_splits;
+  int ab_dtype;            /* dtype of A, B, aux, C2 (simt path; the tc path is bf16 only) */
+} pfn_gemm_desc;
+
+int pfn_gemm_bf16_tc(const pfn_gemm_desc* d, void* stream);
+int pfn_gemm_simt(const pfn_gemm_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Masked multi-head attention under the single_eval_pos mask (mask never materialised):
+ *   keys(i) = {0..sep-1}  U  ({i} if i >= sep)          (reference transformer.py:35-41 generate_D_q_matrix)
+ *   o_i = sum_j softmax_j(q_i.k_j * scale) v_j           (torch:nn/functional.py:6632-6690)
+ * qkv : [T*B, 3*H*dh] packed in-projection output (q | k | v), head h = columns h*dh..(h+1)*dh of each third.
+ * out : [T*B, H*dh];  lse : [B*H, T] fp32 natural-log-sum-exp of the scaled scores (saved for backward).
+ * Backward writes dqkv [T*B, 3*H*dh] completely (no accumulation).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pfn_attn_desc {
+  int T, B, H, dh, sep;
+  int dtype;
+  float scale;
+  const void* qkv; int ld_qkv;
+  void* out; int ld_out;
+  float* lse;
+  const void* dout; int ld_dout;
+  void* dqkv; int ld_dqkv;
+  float* delta;            /* [B*H, T] fp32 scratch for backward: rowsum(dO * O) */
+} pfn_attn_desc;
+
+int pfn_attention_fwd_simt(const pfn_attn_desc* d, void* stream);
+int pfn_attention_bwd_simt(const pfn_attn_desc* d, void* stream);
+int pfn_attention_fwd_tc(const pfn_attn_desc* d, void* stream);
+int pfn_attention_bwd_tc(const pfn_attn_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Embedding stage (reference transformer.py:68-74):
+ *   out[t,b,:] = x[t,b,:] Wx^T + bx + (t < sep ? y[t,b] wy + by : 0)
+ * x [T*B, F] fp32, y [T*B] fp32, Wx [E,F], bx [E], wy [E], by [E] fp32; out [T*B, E] (out_dtype).
+ * Backward accumulates (+=) into dWx, dbx, dwy, dby (fp32).
+ * ---------------------------------------------------------------------------------------------- */
+int pfn_embed_fwd(const float* x, const float* y, const float* Wx, const float* bx, const float* wy, const float* by,
+                  void* out, int out_dtype, int T, int B, int F, int E, int sep, void* stream);
+int pfn_embed_bwd(const void* dout, int dtype, const float* x, const float* y, float* dWx, float* dbx, float* dwy,
+                  float* dby, int T, int B, int F, int E, int sep, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm over the last dim, eps inside the sqrt, biased variance (torch:nn/modules/transformer.py:951-956
+ * norm1/norm2, eps 1e-5).  The residual add is done by the producing GEMM's epilogue, so z = x + sublayer(x).
+ *   fwd : h = (z - mean) * rstd * gamma + beta ; saves mean, rstd (fp32 per row)
+ *   bwd : dz = rstd * (g - mean(g) - xhat * mean(g*xhat)), g = dh*gamma ; dgamma += sum dh*xhat ; dbeta += sum dh
+ *         optional colsum_out[E] += sum_rows dz   (bias gradient of the GEMM that produced z)
+ * ---------------------------------------------------------------------------------------------- */
+int pfn_layernorm_fwd(const void* z, int ldz, const float* gamma, const float* beta, void* h, int ldh, float* mean,
+                      float* rstd, int rows, int E, float eps, int dtype, void* stream);
+int pfn_layernorm_bwd(const void* dh, int lddh, const void* z, int ldz, const float* mean, const float* rstd,
+                      const float* gamma, void* dz, int lddz, float* dgamma, float* dbeta, float* colsum_out, int rows,
+                      int E, int dtype, void* stream);
+
+/* column sums: out[n] += sum_m X[m,n]   (bias gradients; torch autograd of addmm bias) */
+int pfn_colsum(const void* X, int ld, int dtype, float* out, int rows, int N, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Bar-distribution NLL (reference bar_distribution.py:19-33 BarDistribution, :83-108 FullSupport).
+ *   idx  = searchsorted_left(borders, y) - 1 with the two edge fix-ups (:19-23)             -> int64, bit-exact
+ *   nll  = logsumexp(z) - z[idx] + log(width[idx])  (+ half-normal tails when full_support)
+ *   rows with idx outside [0, n_bars) are counted in *oob_count (the reference asserts, :27); FullSupport clamps.
+ * bwd : dlogits[r,:] = g[r] * (softmax(z[r,:]) - onehot(idx[r]))
+ * ---------------------------------------------------------------------------------------------- */
+int pfn_bar_nll_fwd(const void* logits, int ld, int dtype, const float* y, const float* borders, int n_bars,
+                    int full_support, float* nll, int64_t* idx, float* lse, int* oob_count, int rows, void* stream);
+int pfn_bar_nll_bwd(const void* logits, int ld, int dtype, const int64_t* idx, const float* lse, const float* g,
+                    void* dlogits, int ld_d, int d_dtype, int n_bars, int n_cols_pad, int rows, void* stream);
+int pfn_bar_bucket_idx(const float* y, const float* borders, int n_bars, int64_t* idx, int rows, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GP prior sample (reference priors/fast_gp.py:36-58, priors/fast_gp_mix.py:58-134):
+ *   K_b = os_b * k(x_b, x_b; ls_b) + noise_b * I ;  L_b = chol(K_b) ;  y_b = L_b z_b
+ * x [Bn, T, F] fp32, z [Bn, T] fp32, ls [Bn, F], os [Bn], noise [Bn] fp32, y [Bn, T] fp32,
+ * work [Bn, T, T] fp32 scratch (holds L on return), info [Bn] int (0 ok, k>0: pivot k not positive).
+ * jitter is added to every diagonal (gpytorch psd_safe_cholesky retry semantics are driven by the host).
+ * ---------------------------------------------------------------------------------------------- */
+int pfn_gp_sample(const float* x, const float* z, const float* ls, const float* os, const float* noise, float jitter,
+                  int kernel_type, float* y, float* work, int* info, int Bn, int T, int F, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PFN_B200_H_ */

@@ -1,0 +1,396 @@
+// tcgen05 masked attention for the single_eval_pos mask (reference transformer.py:35-41), head dim 128, bf16.
+//
+//   keys(i) = [0, sep)  U  {i if i >= sep}        o_i = softmax_j(q_i.k_j / sqrt(dh)) v_j
+//
+// The [T,T] mask is never built: the dense part (keys < sep) runs on the tensor cores in 64-key blocks and the
+// single diagonal key of a query row is a 128-wide dot product done by the thread that owns the row.
+// Q/K/V tiles are fetched straight out of the packed [T*B, 3E] in-projection output with 3-D TMA descriptors
+// (dims: column, batch, time), so there is no head-split / transpose kernel (the reference spends 22 % of its
+// CPU time in exactly those copies).
+//
+// Forward, per CTA (two CTAs per SM so one CTA's softmax overlaps the other's MMAs):
+//   warp 0      TMA producer: Q tile (128 rows) once per work item, K/V blocks (64 keys) through a 2-stage ring
+//   warp 1      MMA issuer  : S_j = Q K_j^T  (SS, 128x64x128)  ->  TMEM S buffer (double buffered)
+//                             O  += P_j V_j  (TS, P read from TMEM, V MN-major from smem, 128x128x64)
+//   warps 2..5  softmax     : one thread per query row; tcgen05.ld S row, online softmax in the log2 domain with
+//                             lazy rescaling (O is only rescaled when the running max grows by > 2^8), P written
+//                             back to TMEM as packed bf16 over the S buffer; epilogue normalises O and stores.
+// TMEM map (256 columns): [0,64) S0 | [64,128) S1 | [128,256) O ; P_j aliases the first 32 columns of S_j.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "../../include/pfn_b200.h"
+
+namespace pfn {
+
+int check_attn_desc_public(const pfn_attn_desc* d, bool bwd, const char* who);
+
+constexpr int ATT_BM = 128;
+constexpr int ATT_BN = 64;
+constexpr int ATT_DH = 128;
+constexpr int ATT_STAGES = 2;
+constexpr int ATT_THREADS = 192;
+constexpr int ATT_Q_BYTES = ATT_BM * ATT_DH * 2;          // 32 KB (two 64-wide chunks of 16 KB)
+constexpr int ATT_KV_BYTES = ATT_BN * ATT_DH * 2;         // 16 KB per operand (two chunks of 8 KB)
+constexpr int ATT_FWD_SMEM = ATT_Q_BYTES + ATT_STAGES * 2 * ATT_KV_BYTES + 256 + 1024;
+constexpr float kRescaleThreshold = 8.0f;                  // log2 units
+
+struct AttnFwdParams {
+  int T, B, H, sep;
+  float scale_log2;   // scale * log2(e)
+  const __nv_bfloat16* qkv; int ld_qkv;
+  __nv_bfloat16* out; int ld_out;
+  float* lse;
+  int n_qtiles;
+  int total_work;
+};
+
+__device__ __forceinline__ void load_row128(const __nv_bfloat16* p, float (&v)[32], int chunk) {
+  // 32 consecutive bf16 -> fp32 (chunk selects which quarter of the 128-wide row)
+  const uint4* src = reinterpret_cast<const uint4*>(p + chunk * 32);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint4 pk = src[q];
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 t = __bfloat1622float2(h[j]);
+      v[q * 8 + 2 * j] = t.x;
+      v[q * 8 + 2 * j + 1] = t.y;
+    }
+  }
+}
+
+__device__ __forceinline__ float dot_rows128(const __nv_bfloat16* a, const __nv_bfloat16* b) {
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    const uint4 pa = reinterpret_cast<const uint4*>(a)[c];
+    const uint4 pb = reinterpret_cast<const uint4*>(b)[c];
+    const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&pa);
+    const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&pb);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 x = __bfloat1622float2(ha[j]);
+      const float2 y = __bfloat1622float2(hb[j]);
+      acc = fmaf(x.x, y.x, acc);
+      acc = fmaf(x.y, y.y, acc);
+    }
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                   const AttnFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = smem + ATT_Q_BYTES;   // stage s: K at sKV + s*32K, V at +16K
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_Q_BYTES + ATT_STAGES * 2 * ATT_KV_BYTES);
+  uint64_t* q_full = bars + 0;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* kv_full = bars + 2;        // [2]
+  uint64_t* kv_empty = bars + 4;       // [2]
+  uint64_t* s_full = bars + 6;         // [2]
+  uint64_t* p_ready = bars + 8;        // [2]
+  uint64_t* pv_done = bars + 10;
+  uint64_t* o_empty = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int E = p.H * ATT_DH;
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tmQ);
+    tc::tma_prefetch_desc(&tmKV);
+  }
+  if (warp == 1 && lane == 0) {
+    tc::mbar_init(q_full, 1);
+    tc::mbar_init(q_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(&kv_full[s], 1);
+      tc::mbar_init(&kv_empty[s], 1);
+      tc::mbar_init(&s_full[s], 1);
+      tc::mbar_init(&p_ready[s], 128);
+    }
+    tc::mbar_init(pv_done, 1);
+    tc::mbar_init(o_empty, 128);
+    tc::mbar_fence_init();
+  }
+  if (warp == 2) {
+    tc::tmem_alloc(tmem_slot, 256);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int nblk = (p.sep + ATT_BN - 1) / ATT_BN;
+
+  if (warp == 0) {
+    // =============================================================== TMA producer
+    if (lane == 0 && nblk > 0) {
+      uint32_t g = 0;      // running KV-block counter (ring position)
+      uint32_t tcount = 0; // running tile counter
+      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
+        const int bh = w / p.n_qtiles;
+        const int qt = w - bh * p.n_qtiles;
+        const int b = bh / p.H, h = bh - b * p.H;
+        const int i0 = qt * ATT_BM;
+        tc::mbar_wait(q_empty, (tcount & 1) ^ 1);
+        tc::mbar_expect_tx(q_full, ATT_Q_BYTES);
+        tc::tma_load_3d(sQ, &tmQ, q_full, h * ATT_DH, b, i0);
+        tc::tma_load_3d(sQ + 16384, &tmQ, q_full, h * ATT_DH + 64, b, i0);
+        for (int j = 0; j < nblk; ++j, ++g) {
+          const int st = g & 1;
+          tc::mbar_wait(&kv_empty[st], ((g >> 1) & 1) ^ 1);
+          tc::mbar_expect_tx(&kv_full[st], 2 * ATT_KV_BYTES);
+          uint8_t* kdst = sKV + st * 2 * ATT_KV_BYTES;
+          uint8_t* vdst = kdst + ATT_KV_BYTES;
+          const int j0 = j * ATT_BN;
+          tc::tma_load_3d(kdst, &tmKV, &kv_full[st], E + h * ATT_DH, b, j0);
+          tc::tma_load_3d(kdst + 8192, &tmKV, &kv_full[st], E + h * ATT_DH + 64, b, j0);
+          tc::tma_load_3d(vdst, &tmKV, &kv_full[st], 2 * E + h * ATT_DH, b, j0);
+          tc::tma_load_3d(vdst + 8192, &tmKV, &kv_full[st], 2 * E + h * ATT_DH + 64, b, j0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // =============================================================== MMA issuer
+    if (lane == 0 && nblk > 0) {
+      constexpr uint32_t idesc_qk = tc::umma_idesc_bf16(ATT_BM, ATT_BN, 0, 0);
+      constexpr uint32_t idesc_pv = tc::umma_idesc_bf16(ATT_BM, ATT_DH, 0, 1);
+      const uint32_t q_addr = tc::smem_u32(sQ);
+      uint32_t g = 0, tcount = 0;
+      auto issue_qk = [&](uint32_t gg) {
+        const int st = gg & 1;
+        const uint32_t k_addr = tc::smem_u32(sKV + st * 2 * ATT_KV_BYTES);
+        const uint32_t d_tmem = tmem_base + (gg & 1) * ATT_BN;
+#pragma unroll
+        for (int kk = 0; kk < ATT_DH / 16; ++kk) {
+          const uint64_t a_desc = tc::umma_smem_desc(q_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
+          const uint64_t b_desc = tc::umma_smem_desc(k_addr + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024);
+          tc::umma_bf16_ss(d_tmem, a_desc, b_desc, idesc_qk, kk > 0 ? 1u : 0u);
+        }
+      };
+      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
+        tc::mbar_wait(q_full, tcount & 1);
+        tc::mbar_wait(&kv_full[g & 1], (g >> 1) & 1);
+        tc::tc_fence_after();
+        issue_qk(g);
+        tc::umma_commit(&s_full[g & 1]);
+        for (int j = 0; j < nblk; ++j, ++g) {
+          if (j + 1 < nblk) {
+            const uint32_t gn = g + 1;
+            tc::mbar_wait(&kv_full[gn & 1], (gn >> 1) & 1);
+            tc::tc_fence_after();
+            issue_qk(gn);
+            tc::umma_commit(&s_full[gn & 1]);
+          } else {
+            tc::umma_commit(q_empty);   // every QK^T of this tile has been issued
+          }
+          tc::mbar_wait(&p_ready[g & 1], (g >> 1) & 1);
+          if (j == 0) tc::mbar_wait(o_empty, (tcount & 1) ^ 1);
+          tc::tc_fence_after();
+          const int st = g & 1;
+          const uint32_t v_addr = tc::smem_u32(sKV + st * 2 * ATT_KV_BYTES + ATT_KV_BYTES);
+          const uint32_t p_tmem = tmem_base + (g & 1) * ATT_BN;
+          const uint32_t o_tmem = tmem_base + 128;
+#pragma unroll
+          for (int kk = 0; kk < ATT_BN / 16; ++kk) {
+            const uint64_t b_desc = tc::umma_smem_desc(v_addr + kk * 2048, 8192, 1024);
+            tc::umma_bf16_ts(o_tmem, p_tmem + kk * 8, b_desc, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+          }
+          tc::umma_commit(&kv_empty[st]);
+          tc::umma_commit(pv_done);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================================================== softmax / correction / epilogue
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    uint32_t g = 0;
+    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+      const int bh = w / p.n_qtiles;
+      const int qt = w - bh * p.n_qtiles;
+      const int b = bh / p.H, h = bh - b * p.H;
+      const int i = qt * ATT_BM + row;
+      const bool valid = i < p.T;
+      const bool is_query = valid && i >= p.sep;
+      const __nv_bfloat16* tok = p.qkv + (static_cast<size_t>(valid ? i : 0) * p.B + b) * p.ld_qkv + h * ATT_DH;
+      float m = -INFINITY, l = 0.f, t_ii = 0.f;
+      if (is_query) {
+        t_ii = dot_rows128(tok, tok + E) * p.scale_log2;
+        m = t_ii;
+        l = 1.0f;
+      }
+      for (int j = 0; j < nblk; ++j, ++g) {
+        const uint32_t buf = g & 1;
+        tc::mbar_wait(&s_full[buf], (g >> 1) & 1);
+        tc::tc_fence_after();
+        const uint32_t s_tmem = tmem_base + lane_off + buf * ATT_BN;
+        uint32_t r0[32], r1[32];
+        tc::tmem_ld_32x32b_x32(s_tmem, r0);
+        tc::tmem_ld_32x32b_x32(s_tmem + 32, r1);
+        tc::tmem_ld_wait();
+        const int kmax = p.sep - j * ATT_BN;   // number of valid keys in this block (>= 1)
+        float bm = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          if (c < kmax) bm = fmaxf(bm, __uint_as_float(r0[c]));
+          if (c + 32 < kmax) bm = fmaxf(bm, __uint_as_float(r1[c]));
+        }
+        bm *= p.scale_log2;
+        const bool need = bm > m + kRescaleThreshold;   // also true when m == -inf
+        if (__any_sync(0xffffffffu, need)) {
+          const float m_new = need ? bm : m;
+          const float factor = need ? tc::fast_exp2(m - m_new) : 1.0f;   // exp2(-inf) = 0
+          l *= factor;
+          m = m_new;
+          if (j > 0) {
+            tc::mbar_wait(pv_done, (g - 1) & 1);
+            tc::tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+              uint32_t o[32];
+              const uint32_t o_tmem = tmem_base + lane_off + 128 + c * 32;
+              tc::tmem_ld_32x32b_x32(o_tmem, o);
+              tc::tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * factor);
+              tc::tmem_st_32x32b_x32(o_tmem, o);
+            }
+            tc::tmem_st_wait();
+          }
+        }
+        uint32_t pk[32];
+        float psum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const float a0 = (2 * c < kmax) ? tc::fast_exp2(fmaf(__uint_as_float(r0[2 * c]), p.scale_log2, -m)) : 0.f;
+          const float a1 = (2 * c + 1 < kmax) ? tc::fast_exp2(fmaf(__uint_as_float(r0[2 * c + 1]), p.scale_log2, -m)) : 0.f;
+          const float b0 = (2 * c + 32 < kmax) ? tc::fast_exp2(fmaf(__uint_as_float(r1[2 * c]), p.scale_log2, -m)) : 0.f;
+          const float b1 = (2 * c + 33 < kmax) ? tc::fast_exp2(fmaf(__uint_as_float(r1[2 * c + 1]), p.scale_log2, -m)) : 0.f;
+          psum += (a0 + a1) + (b0 + b1);
+          pk[c] = tc::pack_bf16x2(a0, a1);
+          pk[16 + c] = tc::pack_bf16x2(b0, b1);
+        }
+        l += psum;
+        tc::tmem_st_32x32b_x32(tmem_base + lane_off + buf * ATT_BN, pk);
+        tc::tmem_st_wait();
+        tc::tc_fence_before();
+        tc::mbar_arrive(&p_ready[buf]);
+      }
+      // ---- epilogue: O / l (+ diagonal key), lse
+      if (nblk > 0) {
+        tc::mbar_wait(pv_done, (g - 1) & 1);
+        tc::tc_fence_after();
+      }
+      const float pd = is_query ? tc::fast_exp2(t_ii - m) : 0.f;
+      const float inv_l = 1.0f / l;
+      __nv_bfloat16* orow = p.out + (static_cast<size_t>(valid ? i : 0) * p.B + b) * p.ld_out + h * ATT_DH;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float o[32];
+        if (nblk > 0) {
+          uint32_t raw[32];
+          tc::tmem_ld_32x32b_x32(tmem_base + lane_off + 128 + c * 32, raw);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) o[e] = __uint_as_float(raw[e]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) o[e] = 0.f;
+        }
+        if (is_query) {
+          float vv[32];
+          load_row128(tok + 2 * E, vv, c);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) o[e] = fmaf(pd, vv[e], o[e]);
+        }
+        if (valid) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 8) {
+            uint4 pk4;
+            pk4.x = tc::pack_bf16x2(o[e] * inv_l, o[e + 1] * inv_l);
+            pk4.y = tc::pack_bf16x2(o[e + 2] * inv_l, o[e + 3] * inv_l);
+            pk4.z = tc::pack_bf16x2(o[e + 4] * inv_l, o[e + 5] * inv_l);
+            pk4.w = tc::pack_bf16x2(o[e + 6] * inv_l, o[e + 7] * inv_l);
+            *reinterpret_cast<uint4*>(orow + c * 32 + e) = pk4;
+          }
+        }
+      }
+      if (valid) p.lse[static_cast<size_t>(bh) * p.T + i] = (m + log2f(l)) * 0.6931471805599453f;
+      if (nblk > 0) {
+        tc::tc_fence_before();
+        tc::mbar_arrive(o_empty);
+      }
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, 256);
+  }
+}
+
+static int make_qkv_map(CUtensorMap* tm, const void* base, int ld, int width, int B, int T, int box_rows) {
+  uint64_t dims[3] = {static_cast<uint64_t>(width), static_cast<uint64_t>(B), static_cast<uint64_t>(T)};
+  uint64_t strides[3] = {0, static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(ld) * 2 * B};
+  uint32_t box[3] = {64, 1, static_cast<uint32_t>(box_rows)};
+  return make_tensor_map_bf16(tm, base, 3, dims, strides, box, true);
+}
+
+static int check_tc_attn(const pfn_attn_desc* d, const char* who) {
+  PFN_CHECK_ARG(d->dtype == PFN_BF16, "%s: bf16 only", who);
+  PFN_CHECK_ARG(d->dh == ATT_DH, "%s: head dim %d unsupported (tcgen05 path is built for 128)", who, d->dh);
+  PFN_CHECK_ARG(d->ld_qkv % 8 == 0 && d->ld_out % 8 == 0, "%s: leading dims must be multiples of 8", who);
+  PFN_CHECK_ARG(((reinterpret_cast<uintptr_t>(d->qkv) | reinterpret_cast<uintptr_t>(d->out)) & 15) == 0,
+                "%s: qkv/out must be 16-byte aligned", who);
+  return 0;
+}
+
+}  // namespace pfn
+
+using namespace pfn;
+
+extern "C" int pfn_attention_fwd_tc(const pfn_attn_desc* d, void* stream) {
+  if (int rc = check_attn_desc_public(d, false, "attention_fwd_tc")) return rc;
+  if (int rc = check_tc_attn(d, "attention_fwd_tc")) return rc;
+  CUtensorMap tmQ, tmKV;
+  const int E = d->H * d->dh;
+  if (int rc = make_qkv_map(&tmQ, d->qkv, d->ld_qkv, 3 * E, d->B, d->T, ATT_BM)) return rc;
+  if (int rc = make_qkv_map(&tmKV, d->qkv, d->ld_qkv, 3 * E, d->B, d->T, ATT_BN)) return rc;
+  AttnFwdParams p;
+  p.T = d->T; p.B = d->B; p.H = d->H; p.sep = d->sep;
+  p.scale_log2 = d->scale * 1.4426950408889634f;
+  p.qkv = reinterpret_cast<const __nv_bfloat16*>(d->qkv); p.ld_qkv = d->ld_qkv;
+  p.out = reinterpret_cast<__nv_bfloat16*>(d->out); p.ld_out = d->ld_out;
+  p.lse = d->lse;
+  p.n_qtiles = (d->T + ATT_BM - 1) / ATT_BM;
+  p.total_work = p.n_qtiles * d->B * d->H;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PFN_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWD_SMEM));
+    PFN_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    attr_set = true;
+  }
+  int grid = 2 * num_sms();
+  if (grid > p.total_work) grid = p.total_work;
+  attn_fwd_tc_kernel<<<grid, ATT_THREADS, ATT_FWD_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmKV, p);
+  PFN_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int pfn_attention_bwd_tc(const pfn_attn_desc* d, void* stream) {
+  (void)d; (void)stream;
+  set_error("attention_bwd_tc: not built in this revision (use pfn_attention_bwd_simt)");
+  return 4;
+}
