@@ -25,6 +25,8 @@ ICDF_HALFNORMAL_HALF = 0.6744897501960817  # HalfNormal(1).icdf(0.5)  (bar_distr
 def d_q_mask(sz, query_size, dtype=torch.float32):
     """Additive mask M[i, j] = 0 if (j < sz - query_size) or (i == j) else -inf."""
     train = sz - query_size
+    if train < 0:                      # python slice semantics of `mask[:, train_size:]` (transformer.py:38)
+        train = max(sz + train, 0)
     i = torch.arange(sz).unsqueeze(1)
     j = torch.arange(sz).unsqueeze(0)
     allowed = (j < train) | (i == j)

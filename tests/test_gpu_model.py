@@ -1,0 +1,126 @@
+"""End-to-end parity of the CUDA engine (TransformerModel + FullSupportBarDistribution) against the golden outputs
+of the unmodified reference (tests/golden/model_*.pt) and against the CPU oracle.
+Tolerances are the ones BASELINE.json states: NLL within 1e-4 relative in fp32, 1e-2 in bf16."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from transformerscandobayesianinference_b200 import bar_distribution, transformer
+from oracle import pfn_oracle as O
+from oracle.make_golden import MODEL_CASES, build_case_weights, case_inputs, case_borders
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _model(case, precision, dev):
+    ctor = lambda enc, yenc: transformer.TransformerModel(enc, case["n_out"], case["E"], case["H"], case["nhid"],
+                                                          case["L"], 0.0, y_encoder=yenc)
+    m = build_case_weights(ctor, case).to(dev)
+    m.precision = precision
+    return m
+
+
+def _run(case, precision, dev):
+    model = _model(case, precision, dev)
+    x, y = case_inputs(case)
+    x, y = x.to(dev), y.to(dev)
+    crit = bar_distribution.FullSupportBarDistribution(case_borders(case)).to(dev)
+    model.train()
+    logits = model((x, y), single_eval_pos=case["sep"])
+    losses = crit(logits.reshape(-1, case["n_out"]), y[case["sep"]:].flatten()).view(*logits.shape[:2])
+    loss = losses.mean()
+    loss.backward()
+    return model, logits, losses, loss
+
+
+@pytest.mark.parametrize("name", list(MODEL_CASES))
+def test_fp32_engine_matches_reference_golden(cuda_device, name):
+    gold = torch.load(os.path.join(GOLD, f"model_{name}.pt"))
+    case = gold["case"]
+    model, logits, losses, loss = _run(case, "fp32", cuda_device)
+    assert logits.shape == gold["logits"].shape
+    rel = abs(loss.item() - gold["loss"].item()) / abs(gold["loss"].item())
+    assert rel <= 1e-4, f"NLL rel err {rel}"
+    assert (logits.cpu() - gold["logits"]).abs().max().item() <= 5e-4 * gold["logits"].abs().max().item()
+    assert (losses.cpu() - gold["losses"]).abs().max().item() <= 5e-4 * gold["losses"].abs().max().item()
+    for k, p in model.named_parameters():
+        s, a, nrm = gold["grad_checksum"][k]
+        assert p.grad is not None, k
+        got = p.grad.float().cpu()
+        assert abs(got.norm().item() - nrm) <= 2e-3 * nrm + 1e-6, f"{k}: grad norm {got.norm().item()} vs {nrm}"
+        head = gold["grad_samples"][k]
+        assert (got.flatten()[:16] - head).abs().max().item() <= 2e-3 * (head.abs().max().item() + 1e-2 * nrm / got.numel() ** 0.5 + 1e-7), k
+
+
+@pytest.mark.parametrize("name", list(MODEL_CASES))
+def test_bf16_engine_matches_reference_golden(cuda_device, name):
+    gold = torch.load(os.path.join(GOLD, f"model_{name}.pt"))
+    case = gold["case"]
+    model, logits, losses, loss = _run(case, "bf16", cuda_device)
+    rel = abs(loss.item() - gold["loss"].item()) / abs(gold["loss"].item())
+    assert rel <= 1e-2, f"NLL rel err {rel}"
+    for k, p in model.named_parameters():
+        s, a, nrm = gold["grad_checksum"][k]
+        got = p.grad.float().cpu()
+        assert abs(got.norm().item() - nrm) <= 6e-2 * nrm + 1e-5, f"{k}: grad norm {got.norm().item()} vs {nrm}"
+
+
+def test_engine_matches_oracle_full_gradients(cuda_device):
+    """Every gradient element against the fp64 oracle (the golden file only stores checksums)."""
+    case = dict(T=40, B=4, F=3, E=256, nhid=512, L=2, H=2, n_out=50, sep=24, seed=21)
+    model, logits, losses, loss = _run(case, "fp32", cuda_device)
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    P = O.params_from_state_dict(sd, case["L"], torch.float64)
+    leaves = {"encoder.weight": P["enc_w"], "y_encoder.weight": P["yenc_w"], "decoder.0.weight": P["dec_w0"],
+              "decoder.2.bias": P["dec_b2"]}
+    for i, lp in enumerate(P["layers"]):
+        pre = f"transformer_encoder.layers.{i}."
+        leaves.update({pre + "self_attn.in_proj_weight": lp["in_w"], pre + "self_attn.in_proj_bias": lp["in_b"],
+                       pre + "self_attn.out_proj.weight": lp["out_w"], pre + "self_attn.out_proj.bias": lp["out_b"],
+                       pre + "linear1.weight": lp["w1"], pre + "linear1.bias": lp["b1"], pre + "linear2.weight": lp["w2"],
+                       pre + "linear2.bias": lp["b2"], pre + "norm1.weight": lp["g1"], pre + "norm1.bias": lp["be1"],
+                       pre + "norm2.weight": lp["g2"], pre + "norm2.bias": lp["be2"]})
+    for t in leaves.values():
+        t.requires_grad_(True)
+    x, y = case_inputs(case)
+    ref_logits = O.transformer_forward_ref(P, x.double(), y.double(), case["sep"], case["H"])
+    ref_nll = O.bar_nll_ref(ref_logits.reshape(-1, case["n_out"]), y[case["sep"]:].flatten().double(),
+                            case_borders(case).double(), full_support=True)
+    ref_nll.mean().backward()
+    assert abs(loss.item() - ref_nll.mean().item()) <= 1e-4 * abs(ref_nll.mean().item())
+    named = dict(model.named_parameters())
+    for k, t in leaves.items():
+        got = named[k].grad.double().cpu()
+        denom = t.grad.abs().max().item() + 1e-9
+        assert (got - t.grad).abs().max().item() <= 2e-3 * denom, f"{k}: {(got - t.grad).abs().max().item()} vs scale {denom}"
+
+
+def test_eval_mode_inference_and_negative_sep(cuda_device):
+    case = MODEL_CASES["sep_last"]
+    model = _model(case, "fp32", cuda_device).eval()
+    x, y = case_inputs(case)
+    x, y = x.to(cuda_device), y.to(cuda_device)
+    with torch.inference_mode():
+        a = model((x, y), single_eval_pos=-1)
+        b = model((x, y), single_eval_pos=case["T"] - 1)
+    assert a.shape == (1, case["B"], case["n_out"]) and torch.equal(a, b)
+
+
+def test_generic_encoder_path(cuda_device):
+    """Non-fused embedding (positional encoding present) still runs through the CUDA stack and back-propagates."""
+    from transformerscandobayesianinference_b200 import encoders, positional_encodings
+    torch.manual_seed(0)
+    m = transformer.TransformerModel(encoders.Linear(2, 64), 5, 64, 2, 128, 2, 0.0, y_encoder=encoders.Linear(1, 64),
+                                     pos_encoder=positional_encodings.PositionalEncoding(64, 100)).to(cuda_device)
+    m.precision = "fp32"
+    with torch.no_grad():
+        for l in m.transformer_encoder.layers:
+            l.linear2.weight.normal_(0, 0.05); l.self_attn.out_proj.weight.normal_(0, 0.05)
+    x, y = torch.rand(9, 3, 2, device=cuda_device), torch.randn(9, 3, device=cuda_device)
+    out = m((x, y), single_eval_pos=4)
+    out.square().mean().backward()
+    assert out.shape == (5, 3, 5)
+    assert m.encoder.weight.grad.abs().sum() > 0 and m.transformer_encoder.layers[0].linear1.weight.grad.abs().sum() > 0

@@ -1,0 +1,113 @@
+"""The reference-shaped `train.train` loop on the GPU with the fused GP prior, plus sampler statistics."""
+import random
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from transformerscandobayesianinference_b200 import bar_distribution, encoders, priors, train as train_mod, utils
+from oracle import pfn_oracle as O
+
+
+def test_fast_gp_get_batch_contract_and_covariance(cuda_device):
+    torch.manual_seed(0)
+    hps = {"noise": 0.1, "outputscale": 0.5, "lengthscale": 0.3}
+    x, y, t = priors.fast_gp.get_batch(64, 30, 2, device="cuda:0", hyperparameters=hps)
+    assert x.shape == (30, 64, 2) and y.shape == (30, 64) and t is y and x.is_cuda
+    assert 0 <= x.min() and x.max() < 1
+    # distributional check: fixed x, many z draws -> empirical covariance ~ K + noise I
+    B, T = 4096, 12
+    xs = torch.rand(1, T, 1, device=cuda_device).repeat(B, 1, 1).contiguous()
+    z = torch.randn(B, T, device=cuda_device)
+    ls = torch.full((B, 1), 0.3, device=cuda_device)
+    ys = priors.fast_gp.sample_gp(xs, z, ls, torch.full((B,), 0.5, device=cuda_device), torch.full((B,), 0.1, device=cuda_device))
+    emp = (ys.t() @ ys / B).cpu().double()
+    K = O.gp_kernel_ref(xs[:1].cpu().double(), ls[:1].cpu().double(), torch.tensor([0.5]).double(), torch.tensor([0.1]).double())[0]
+    assert (emp - K).abs().max().item() < 0.06
+    # tuple hyperparameters and cpu output device (sampling still runs on the GPU kernel)
+    x2, y2, _ = priors.fast_gp.get_batch(4, 10, 1, device="cpu", hyperparameters=(0.1, 0.1, 0.1))
+    assert x2.device.type == "cpu" and y2.shape == (10, 4)
+    x3, _, _ = priors.fast_gp.get_batch(2, 8, 1, device="cuda:0", equidistant_x=True)
+    assert torch.allclose(x3[:, 0, 0].cpu(), torch.linspace(0, 1, 8))
+
+
+def test_fast_gp_notebook_hyperparameters_are_factorisable(cuda_device):
+    """noise 1e-4 / outputscale 1 / lengthscale .6 (SetupForGPFittingExperiments.ipynb) at T=1000: cond ~ 1e7."""
+    torch.manual_seed(1)
+    hps = {"noise": 1e-4, "outputscale": 1., "lengthscale": .6, "fast_computations": (False, False, False)}
+    x, y, _ = priors.fast_gp.get_batch(8, 1000, 1, device="cuda:0", hyperparameters=hps)
+    assert torch.isfinite(y).all() and 0.2 < y.std().item() < 3.0
+
+
+def test_fast_gp_mix_hyperprior_moments_and_batch(cuda_device):
+    torch.manual_seed(2)
+    ls, os_, noise = priors.fast_gp_mix.sample_hyperparameters(20000, 2, {}, cuda_device)
+    assert ls.mean().item() == pytest.approx(3.0 / 6.0, rel=0.05)          # Gamma(3, 6) mean
+    assert os_.mean().item() == pytest.approx(0.5 / 0.15, rel=0.08)        # Gamma(.5, .15) mean
+    assert noise.mean().item() == pytest.approx(1.1 / 0.05, rel=0.05)      # Gamma(1.1, .05) mean
+    x, y, t = priors.fast_gp_mix.get_batch(16, 40, 3, device="cuda:0", batch_size_per_gp_sample=4)
+    assert x.shape == (40, 16, 3) and y.shape == (40, 16) and torch.isfinite(y).all()
+    x, y, _ = priors.fast_gp_mix.get_batch(8, 20, 1, device="cuda:0", batch_size_per_gp_sample=4,
+                                           hyperparameters={"sigmoid": True}, fix_to_range=(0.0, 1.0))
+    assert x.shape == (20, 8, 1) and (y >= 0).all() and (y < 1).all()
+
+
+def test_mlp_prior_batch(cuda_device):
+    import numpy as np
+    np.random.seed(0); random.seed(0); torch.manual_seed(0)
+    su = priors.utils
+    hps = (lambda: 3, su.scaled_beta_sampler_f(2, 4, 50, 4), torch.nn.Tanh, su.gamma_sampler_f(3.62, .0677),
+           su.gamma_sampler_f(1.87, .0528), lambda: 0.1, True, su.scaled_beta_sampler_f(1, 1.6, 6, 2), None, False, None,
+           None, None, True, True, lambda n: ([], []), 0.0)
+    x, y, t = priors.mlp.get_batch(16, 32, 6, device="cuda:0", hyperparameters=hps, batch_size_per_gp_sample=4)
+    assert x.shape == (32, 16, 6) and y.shape == (32, 16)
+    assert set(y.unique().tolist()) <= {0.0, 1.0} and 0.3 < y.mean().item() < 0.7
+
+
+def _train_kwargs(crit):
+    return dict(criterion=crit, encoder_generator=encoders.Linear, emsize=128, nhid=256, nlayers=2, nhead=4, dropout=0.0,
+                epochs=3, steps_per_epoch=8, batch_size=16, bptt=30, lr=1e-3, warmup_epochs=1,
+                y_encoder_generator=encoders.Linear,
+                extra_prior_kwargs_dict={"num_features": 1, "hyperparameters": {"noise": .1, "outputscale": .1, "lengthscale": .1}},
+                single_eval_pos_gen=utils.get_weighted_single_eval_pos_sampler(30), verbose=False)
+
+
+def test_train_loop_runs_and_learns(cuda_device):
+    torch.manual_seed(0); random.seed(0)
+    ys = priors.fast_gp.get_batch(500, 30, 1, device="cuda:0")[1]
+    crit = bar_distribution.FullSupportBarDistribution(bar_distribution.get_bucket_limits(100, ys=ys.cpu()))
+    kw = _train_kwargs(crit)
+    kw.update(epochs=6, steps_per_epoch=20, warmup_epochs=1)
+    total_loss, pos_losses, model = train_mod.train(priors.fast_gp.DataLoader, **kw)
+    assert next(model.parameters()).device.type == "cpu"            # returned on CPU like the reference (train.py:135)
+    assert len(pos_losses) == 30 and total_loss == total_loss
+    # the prior's marginal entropy is ~ -0.5; an untrained bar head starts near log(range/bars) ... just require progress
+    kw2 = _train_kwargs(crit); kw2.update(epochs=1, steps_per_epoch=4, warmup_epochs=0, lr=0.0)
+    torch.manual_seed(0); random.seed(0)
+    first_loss, _, _ = train_mod.train(priors.fast_gp.DataLoader, **kw2)
+    assert total_loss < first_loss - 0.05, (first_loss, total_loss)
+
+
+def test_train_gradient_accumulation_equals_big_batch(cuda_device):
+    """aggregate_k_gradients sums un-normalised micro-batch gradients (reference train.py:92-97)."""
+    from transformerscandobayesianinference_b200 import transformer
+    torch.manual_seed(3)
+    dev = cuda_device
+    m = transformer.TransformerModel(encoders.Linear(1, 64), 20, 64, 2, 128, 2, 0.0, y_encoder=encoders.Linear(1, 64)).to(dev)
+    m.precision = "fp32"
+    with torch.no_grad():
+        for l in m.transformer_encoder.layers:
+            l.linear2.weight.normal_(0, 0.05); l.self_attn.out_proj.weight.normal_(0, 0.05)
+    crit = bar_distribution.FullSupportBarDistribution(torch.linspace(-3, 3, 21)).to(dev)
+    x, y = torch.rand(16, 8, 1, device=dev), torch.randn(16, 8, device=dev).clamp(-2.5, 2.5)
+
+    def grads(xs, ys):
+        m.zero_grad()
+        out = m((xs, ys), single_eval_pos=9)
+        crit(out.reshape(-1, 20), ys[9:].flatten()).mean().backward()
+        return [p.grad.clone() for p in m.parameters()]
+    full = grads(x, y)
+    a, b = grads(x[:, :4], y[:, :4]), grads(x[:, 4:], y[:, 4:])
+    for f, ga, gb in zip(full, a, b):
+        assert torch.allclose(f, (ga + gb) / 2, atol=2e-5, rtol=1e-3)   # two half-batches averaged == full-batch mean

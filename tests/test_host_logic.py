@@ -1,0 +1,180 @@
+"""CPU tests of the host-side mirror of the reference API (no CUDA needed): schedules, samplers, bucket limits,
+bar-distribution inference helpers, state_dict compatibility, DataLoader adapter, and loud failure on CPU."""
+import os
+import random
+
+import pytest
+import torch
+from torch import nn
+
+import transformerscandobayesianinference_b200 as pfn
+from transformerscandobayesianinference_b200 import bar_distribution, encoders, positional_encodings, transformer, utils
+from transformerscandobayesianinference_b200.priors import utils as putils
+from oracle.make_golden import MODEL_CASES, build_case_weights, checksum
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_schedules_and_samplers_match_reference():
+    g = torch.load(os.path.join(GOLD, "utils.pt"))
+    opt = torch.optim.SGD([nn.Parameter(torch.zeros(1))], lr=1.0)
+    s = utils.get_cosine_schedule_with_warmup(opt, 3, 10)
+    got = []
+    for _ in range(12):
+        got.append(s.get_last_lr()[0]); opt.step(); s.step()
+    assert got == pytest.approx(g["cosine"], abs=1e-12)
+    assert got[0] == 0.0      # lr is 0 for the whole first epoch when warmup > 0 (reference train.py:56,134)
+    opt = torch.optim.SGD([nn.Parameter(torch.zeros(1))], lr=1.0)
+    s = utils.get_linear_schedule_with_warmup(opt, 2, 8)
+    got = []
+    for _ in range(10):
+        got.append(s.get_last_lr()[0]); opt.step(); s.step()
+    assert got == pytest.approx(g["linear"], abs=1e-12)
+    random.seed(1234)
+    f = utils.get_weighted_single_eval_pos_sampler(50)
+    assert [f() for _ in range(32)] == g["weighted_sep"]
+    random.seed(1234)
+    f = utils.get_uniform_single_eval_pos_sampler(50)
+    assert [f() for _ in range(32)] == g["uniform_sep"]
+    m = nn.Linear(1000, 13246)
+    assert utils.get_openai_lr(m) == pytest.approx(g["openai_lr"], rel=1e-12)
+
+
+def test_mask_helper_matches_reference():
+    gold = torch.load(os.path.join(GOLD, "mask.pt"))
+    for key, ref in gold.items():
+        sz, q = map(int, key.split("_"))
+        assert torch.equal(transformer.TransformerModel.generate_D_q_matrix(sz, q), ref), key
+
+
+def test_bucket_limits_and_inference_helpers_match_reference():
+    gold = torch.load(os.path.join(GOLD, "bar.pt"))
+    lim = bar_distribution.get_bucket_limits(10, ys=gold["limits_from_ys"]["ys"].clone())
+    assert torch.equal(lim, gold["limits_from_ys"]["limits"])
+    assert torch.allclose(bar_distribution.get_bucket_limits(8, full_range=(-2.0, 6.0)), gold["limits_from_range"])
+    for n_bars in (7, 100, 1000):
+        e = gold[n_bars]
+        bd = bar_distribution.BarDistribution(e["borders"])
+        assert bd.num_bars == n_bars
+        assert torch.allclose(bd.mean(e["logits"]), e["mean"], atol=1e-5)
+        assert torch.allclose(bd.mode(e["logits"]), e["mode"])
+        assert torch.allclose(bd.quantile(e["logits"]), e["quantile"], atol=1e-4, equal_nan=True)
+        assert torch.allclose(bd.ei(e["logits"], 0.3, True), e["ei_max"], atol=1e-5)
+        assert torch.allclose(bd.ei(e["logits"], 0.3, False), e["ei_min"], atol=1e-5)
+        fs = bar_distribution.FullSupportBarDistribution(e["borders"])
+        assert torch.allclose(fs.mean(e["logits"]), e["mean_full"], atol=1e-5)
+    with pytest.raises(AssertionError):
+        bar_distribution.BarDistribution(torch.tensor([0., 2., 1.]))
+
+
+def _my_model(case):
+    ctor = lambda enc, yenc: transformer.TransformerModel(enc, case["n_out"], case["E"], case["H"], case["nhid"],
+                                                          case["L"], 0.0, y_encoder=yenc)
+    return build_case_weights(ctor, case)
+
+
+@pytest.mark.parametrize("name", ["cfg1_small", "dh128"])
+def test_model_construction_reproduces_reference_init(name):
+    """Same seed => same weights as the reference model (RNG order, deep-copied layers, zero-init), proven by the
+    reference state_dict checksum stored in the golden file."""
+    gold = torch.load(os.path.join(GOLD, f"model_{name}.pt"))
+    cs = checksum(_my_model(gold["case"]).state_dict())
+    assert set(cs) == set(gold["weights_checksum"])
+    for k, (s, a) in gold["weights_checksum"].items():
+        assert cs[k][0] == pytest.approx(s, rel=1e-9, abs=1e-9) and cs[k][1] == pytest.approx(a, rel=1e-9), k
+
+
+def test_fresh_model_zero_init_and_identical_layers():
+    torch.manual_seed(0)
+    m = transformer.TransformerModel(encoders.Linear(3, 64), 10, 64, 2, 128, 3, 0.0, y_encoder=encoders.Linear(1, 64))
+    l0, l2 = m.transformer_encoder.layers[0], m.transformer_encoder.layers[2]
+    assert l0.linear2.weight.abs().sum() == 0 and l0.self_attn.out_proj.weight.abs().sum() == 0
+    assert torch.equal(l0.linear1.weight, l2.linear1.weight) and torch.equal(l0.self_attn.in_proj_weight, l2.self_attn.in_proj_weight)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/results"), reason="reference checkpoints only exist in the build container")
+def test_reference_checkpoints_load_strict():
+    res = "/root/reference/results"
+    for fn in sorted(os.listdir(res)):
+        sd = torch.load(os.path.join(res, fn), map_location="cpu", weights_only=False)[0]
+        E = sd["encoder.weight"].shape[0]
+        F = sd["encoder.weight"].shape[1]
+        nhid = sd["transformer_encoder.layers.0.linear1.weight"].shape[0]
+        L = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("transformer_encoder.layers."))
+        n_out = sd["decoder.2.weight"].shape[0]
+        m = transformer.TransformerModel(encoders.Linear(F, E), n_out, E, 4, nhid, L, 0.0, y_encoder=encoders.Linear(1, E))
+        m.load_state_dict(sd, strict=True)
+
+
+def test_forward_on_cpu_fails_loudly():
+    m = transformer.TransformerModel(encoders.Linear(1, 32), 5, 32, 2, 64, 1, 0.0, y_encoder=encoders.Linear(1, 32))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m((torch.rand(4, 2, 1), torch.rand(4, 2)), single_eval_pos=2)
+    bd = bar_distribution.BarDistribution(torch.linspace(-1, 1, 6))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        bd(torch.zeros(3, 5), torch.zeros(3))
+
+
+def test_dataloader_adapter_contract():
+    calls = []
+
+    def gb(batch_size, seq_len, num_features, scale=1.0):
+        calls.append((batch_size, seq_len, num_features, scale))
+        x = torch.rand(seq_len, batch_size, num_features)
+        y = x.sum(-1) * scale
+        return x, y, y
+
+    DL = putils.get_batch_to_dataloader(gb)
+    DL.num_outputs = 1
+    dl = DL(num_steps=3, batch_size=4, seq_len=5, num_features=2, scale=2.0)
+    assert len(dl) == 3 and dl.num_features == 2 and dl.num_outputs == 1 and dl.fuse_x_y is False
+    batches = list(dl)
+    assert len(batches) == 3 and len(calls) == 3 and calls[0] == (4, 5, 2, 2.0)
+    (x, y), t = batches[0]
+    assert x.shape == (5, 4, 2) and y.shape == (5, 4) and torch.equal(y, t)
+    fused, t = DL.gbm(batch_size=4, seq_len=5, num_features=2, fuse_x_y=True)
+    assert fused.shape == (5, 4, 3) and (fused[0, :, -1] == 0).all()
+    assert DL.get_batch_method is not None
+
+
+def test_normalize_binarize_order_helpers():
+    torch.manual_seed(0)
+    d = torch.randn(50, 3, 2) * 4 + 1
+    n = putils.normalize_data(d)
+    assert torch.allclose(n.mean(0), torch.zeros(3, 2), atol=1e-5) and torch.allclose(n.std(0), torch.ones(3, 2), atol=1e-3)
+    b = putils.Binarize()(torch.tensor([1., 2., 3., 4.]))
+    assert b.tolist() == [0., 0., 1., 1.]          # torch.median = lower median
+    random.seed(0)
+    x, y = torch.rand(6, 1, 2), torch.tensor([3., 1., 2., 6., 5., 4.]).view(6, 1, 1)
+    xo, yo = putils.order_by_y(x, y)
+    assert sorted(yo.flatten().tolist()) == [1., 2., 3., 4., 5., 6.]
+
+
+def test_positional_encodings_and_encoders():
+    pe = positional_encodings.PositionalEncoding(8, max_len=16)
+    assert pe.pe.shape == (16, 1, 8)
+    x = torch.zeros(4, 2, 8)
+    assert torch.allclose(pe(x)[:, 0, 0], torch.sin(torch.arange(4.)))
+    assert positional_encodings.NoPositionalEncoding(8, 16)(x) is x
+    assert positional_encodings.LearnedPositionalEncoding(8, 16)(x).shape == x.shape
+    assert positional_encodings.PairedScrambledPositionalEncodings(8, 16)(x).shape == x.shape
+    ce = encoders.get_Canonical(5)(2, 8)
+    assert ce(torch.randint(0, 5, (4, 3, 2))).shape == (4, 3, 8)
+    assert encoders.Linear is nn.Linear
+
+
+def test_install_dropin_registers_reference_module_names():
+    import sys
+    saved = {k: sys.modules.get(k) for k in ("train", "transformer", "bar_distribution", "priors", "encoders", "utils", "positional_encodings")}
+    try:
+        mods = pfn.install_dropin()
+        import train as t, priors as p, bar_distribution as b  # noqa: E401
+        assert t.train is mods["train"].train and hasattr(p, "fast_gp") and hasattr(b, "FullSupportBarDistribution")
+        assert hasattr(t, "Losses") and hasattr(t, "get_weighted_single_eval_pos_sampler")
+        assert hasattr(p.fast_gp, "DataLoader") and p.fast_gp.DataLoader.num_outputs == 1
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v

@@ -1,0 +1,243 @@
+"""The PFN step engine: explicit forward/backward of the post-norm GELU encoder stack, the embedding stage and
+the decoder head, expressed as sequences of C-ABI kernel calls (libpfn_b200.so) and exposed to PyTorch as three
+`torch.autograd.Function`s so that `loss.backward()` in the reference-shaped `train.train` keeps working.
+
+Restates what the reference obtains from `nn.TransformerEncoder` (reference transformer.py:17-18,84;
+torch nn/modules/transformer.py:951-982) — see SURVEY.md Appendix A.1 for the maths.
+
+Layout: activations are [T*B, cols] row-major with token row = t*B + b (the reference's sequence-first layout,
+flattened), in the activation dtype (bf16 by default, fp32 in parity mode).  Parameters stay fp32 masters; the
+bf16 mode casts them once per forward.  Weight gradients are produced in fp32 by split-K tensor-core GEMMs that
+read dY and X *in place* as MN-major operands (no transposed copies).
+"""
+import os
+
+import torch
+
+from . import _lib as L
+
+LAYER_PARAM_NAMES = ("in_w", "in_b", "out_w", "out_b", "w1", "b1", "w2", "b2", "g1", "be1", "g2", "be2")
+N_LAYER_PARAMS = len(LAYER_PARAM_NAMES)
+LN_EPS = 1e-5
+
+
+def default_precision():
+    return os.environ.get("PFN_B200_PRECISION", "bf16")
+
+
+def act_dtype(precision):
+    if precision == "bf16":
+        return torch.bfloat16
+    if precision == "fp32":
+        return torch.float32
+    raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+
+
+def _wgrad_splits(n_tokens, out_rows, out_cols):
+    """k-splits so that tiles * splits ~ fills the SMs a few times over (contraction runs over the tokens)."""
+    tiles = ((out_rows + 127) // 128) * ((out_cols + 255) // 256 if out_cols > 128 else 1)
+    num_kb = (n_tokens + 63) // 64
+    want = max(1, (4 * 148) // max(tiles, 1))
+    return max(1, min(want, num_kb // 8 if num_kb >= 16 else 1))
+
+
+def _cast(w, dtype):
+    w = w.detach()
+    return w.contiguous() if w.dtype == dtype else w.to(dtype).contiguous()
+
+
+def _linear_fwd(x, w_c, bias, *, aux=None, epilogue=L.EPI_NONE, want_pre=False, out_dtype=None):
+    """y = epi(x @ w_c^T + bias) (+aux).  x [M,K], w_c [N,K] (activation dtype)."""
+    M, N = x.shape[0], w_c.shape[0]
+    y = torch.empty(M, N, device=x.device, dtype=out_dtype or x.dtype)
+    pre = torch.empty(M, N, device=x.device, dtype=x.dtype) if want_pre else None
+    L.gemm(x, w_c, y, bias=bias, aux=aux, C2=pre, epilogue=epilogue)
+    return (y, pre) if want_pre else y
+
+
+def _linear_dgrad(dy, w_c, *, aux=None, epilogue=L.EPI_NONE):
+    """dx = dy @ w_c (+aux | * gelu'(aux)).  dy [M,N], w_c [N,K] read as an MN-major B operand."""
+    M, K = dy.shape[0], w_c.shape[1]
+    dx = torch.empty(M, K, device=dy.device, dtype=dy.dtype)
+    L.gemm(dy, w_c, dx, b_mn_major=True, aux=aux, epilogue=epilogue, M=M, N=K, K=w_c.shape[0])
+    return dx
+
+
+def _linear_wgrad(dy, x, dw, rows=None, cols=None):
+    """dw[N,K] += dy^T @ x.  dy [M,N], x [M,K] both read in place as MN-major operands; fp32 atomic split-K."""
+    n_tok = dy.shape[0]
+    N = dw.shape[0] if rows is None else rows
+    K = dw.shape[1] if cols is None else cols
+    L.gemm(dy, x, dw, a_mn_major=True, b_mn_major=True, accumulate=True, k_splits=_wgrad_splits(n_tok, N, K),
+           M=N, N=K, K=n_tok)
+
+
+class EncoderStackFn(torch.autograd.Function):
+    """src [T*B, E] (activation dtype) -> output of `nlayers` post-norm encoder layers under the sep mask."""
+
+    @staticmethod
+    def forward(ctx, src, T, B, sep, nhead, precision, *params):
+        L.require_cuda(src, *params)
+        dt = act_dtype(precision)
+        assert src.dtype == dt and src.dim() == 2
+        n_layers = len(params) // N_LAYER_PARAMS
+        N, E = src.shape
+        dh = E // nhead
+        keep = torch.is_grad_enabled() and (src.requires_grad or any(p.requires_grad for p in params))
+        saved = []
+        h = src.contiguous()
+        for li in range(n_layers):
+            P = dict(zip(LAYER_PARAM_NAMES, params[li * N_LAYER_PARAMS:(li + 1) * N_LAYER_PARAMS]))
+            in_w, out_w, w1, w2 = (_cast(P[k], dt) for k in ("in_w", "out_w", "w1", "w2"))
+            qkv = _linear_fwd(h, in_w, P["in_b"])
+            attn = torch.empty(N, E, device=h.device, dtype=dt)
+            lse = torch.empty(B * nhead, T, device=h.device, dtype=torch.float32)
+            L.attention_fwd(qkv, attn, lse, T, B, nhead, dh, sep)
+            z1 = _linear_fwd(attn, out_w, P["out_b"], aux=h)
+            h1 = torch.empty_like(z1)
+            mean1 = torch.empty(N, device=h.device, dtype=torch.float32)
+            rstd1 = torch.empty_like(mean1)
+            L.layernorm_fwd(z1, P["g1"], P["be1"], h1, mean1, rstd1, LN_EPS)
+            g, u = _linear_fwd(h1, w1, P["b1"], epilogue=L.EPI_GELU, want_pre=True)
+            z2 = _linear_fwd(g, w2, P["b2"], aux=h1)
+            h2 = torch.empty_like(z2)
+            mean2 = torch.empty_like(mean1)
+            rstd2 = torch.empty_like(mean1)
+            L.layernorm_fwd(z2, P["g2"], P["be2"], h2, mean2, rstd2, LN_EPS)
+            if keep:
+                saved.append((h, qkv, attn, lse, z1, mean1, rstd1, h1, u, g, z2, mean2, rstd2))
+            h = h2
+        ctx.saved_acts = saved
+        ctx.params = params
+        ctx.meta = (T, B, sep, nhead, precision, n_layers)
+        return h
+
+    @staticmethod
+    def backward(ctx, dout):
+        T, B, sep, nhead, precision, n_layers = ctx.meta
+        dt = act_dtype(precision)
+        params = ctx.params
+        dev = dout.device
+        N, E = dout.shape
+        dh = E // nhead
+        sizes = [p.numel() for p in params]
+        flat = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
+        grads, off = [], 0
+        for p, n in zip(params, sizes):
+            grads.append(flat[off:off + n].view(p.shape))
+            off += n
+        dh2 = dout.contiguous().to(dt)
+        for li in reversed(range(n_layers)):
+            P = dict(zip(LAYER_PARAM_NAMES, params[li * N_LAYER_PARAMS:(li + 1) * N_LAYER_PARAMS]))
+            G = dict(zip(LAYER_PARAM_NAMES, grads[li * N_LAYER_PARAMS:(li + 1) * N_LAYER_PARAMS]))
+            h, qkv, attn, lse, z1, mean1, rstd1, h1, u, g, z2, mean2, rstd2 = ctx.saved_acts[li]
+            ctx.saved_acts[li] = None
+            in_w, out_w, w1, w2 = (_cast(P[k], dt) for k in ("in_w", "out_w", "w1", "w2"))
+            # ---- LN2 and the MLP
+            dz2 = torch.empty_like(z2)
+            L.layernorm_bwd(dh2, z2, mean2, rstd2, P["g2"], dz2, G["g2"], G["be2"], G["b2"])
+            del dh2, z2
+            _linear_wgrad(dz2, g, G["w2"])
+            du = _linear_dgrad(dz2, w2, aux=u, epilogue=L.EPI_GELU_BWD)
+            del g, u
+            L.colsum(du, G["b1"])
+            _linear_wgrad(du, h1, G["w1"])
+            dh1 = _linear_dgrad(du, w1, aux=dz2)
+            del du, dz2, h1
+            # ---- LN1 and attention
+            dz1 = torch.empty_like(z1)
+            L.layernorm_bwd(dh1, z1, mean1, rstd1, P["g1"], dz1, G["g1"], G["be1"], G["out_b"])
+            del dh1, z1
+            _linear_wgrad(dz1, attn, G["out_w"])
+            dattn = _linear_dgrad(dz1, out_w)
+            dqkv = torch.empty_like(qkv)
+            delta = torch.empty_like(lse)
+            L.attention_bwd(qkv, attn, lse, dattn, dqkv, delta, T, B, nhead, dh, sep, use_tc=False)
+            del dattn, attn, qkv
+            L.colsum(dqkv, G["in_b"])
+            _linear_wgrad(dqkv, h, G["in_w"])
+            dh2 = _linear_dgrad(dqkv, in_w, aux=dz1)
+            del dqkv, dz1, h
+        ctx.saved_acts = None
+        return (dh2, None, None, None, None, None) + tuple(grads)
+
+
+class EmbedFn(torch.autograd.Function):
+    """(x [T,B,F], y [T,B]) -> src [T*B, E]:  x Wx^T + bx + (t < sep)(y wy + by)   (reference transformer.py:68-74)."""
+
+    @staticmethod
+    def forward(ctx, x, y, Wx, bx, wy, by, sep, precision):
+        L.require_cuda(x, y, Wx, bx, wy, by)
+        T, B, F = x.shape
+        E = Wx.shape[0]
+        x = x.detach().contiguous().float()
+        y = y.detach().contiguous().float()
+        out = torch.empty(T * B, E, device=x.device, dtype=act_dtype(precision))
+        L.embed_fwd(x, y, Wx.detach().contiguous(), bx.detach().contiguous(), wy.detach().contiguous().view(-1),
+                    by.detach().contiguous(), out, T, B, F, E, sep)
+        ctx.save_for_backward(x, y)
+        ctx.meta = (T, B, F, E, sep, wy.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, y = ctx.saved_tensors
+        T, B, F, E, sep, wy_shape = ctx.meta
+        dev = dout.device
+        dWx = torch.zeros(E, F, device=dev)
+        dbx = torch.zeros(E, device=dev)
+        dwy = torch.zeros(E, device=dev)
+        dby = torch.zeros(E, device=dev)
+        L.embed_bwd(dout.contiguous(), x, y, dWx, dbx, dwy, dby, T, B, F, E, sep)
+        return None, None, dWx, dbx, dwy.view(wy_shape), dby, None, None
+
+
+class DecoderFn(torch.autograd.Function):
+    """hq [Nq, E] -> logits [Nq, n_out] fp32:  GELU(hq W0^T + b0) W2^T + b2  (reference transformer.py:23,85),
+    applied to the query rows only (the reference computes all T rows and slices, transformer.py:91)."""
+
+    @staticmethod
+    def forward(ctx, hq, W0, b0, W2, b2, precision):
+        L.require_cuda(hq, W0, b0, W2, b2)
+        dt = act_dtype(precision)
+        hq = hq.contiguous()
+        w0, w2 = _cast(W0, dt), _cast(W2, dt)
+        n_out = W2.shape[0]
+        g, u = _linear_fwd(hq, w0, b0, epilogue=L.EPI_GELU, want_pre=True)
+        ld = (n_out + 3) // 4 * 4
+        logits_buf = torch.empty(hq.shape[0], ld, device=hq.device, dtype=torch.float32)
+        logits = logits_buf[:, :n_out]
+        L.gemm(g, w2, logits, bias=b2.detach().contiguous())
+        ctx.save_for_backward(hq, u, g, W0, W2)
+        ctx.precision = precision
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        hq, u, g, W0, W2 = ctx.saved_tensors
+        dt = act_dtype(ctx.precision)
+        dev = dlogits.device
+        Nq, n_out = dlogits.shape
+        w0, w2 = _cast(W0, dt), _cast(W2, dt)
+        ld = (n_out + 7) // 8 * 8
+        dl = torch.zeros(Nq, ld, device=dev, dtype=dt)
+        dl[:, :n_out] = dlogits
+        dlv = dl[:, :n_out]
+        dW2 = torch.zeros_like(W2, dtype=torch.float32)
+        db2 = torch.zeros(n_out, device=dev)
+        dW0 = torch.zeros_like(W0, dtype=torch.float32)
+        db0 = torch.zeros(W0.shape[0], device=dev)
+        L.colsum(dlv, db2)
+        _linear_wgrad(dlv, g, dW2)
+        du = _linear_dgrad(dlv, w2, aux=u, epilogue=L.EPI_GELU_BWD)
+        L.colsum(du, db0)
+        _linear_wgrad(du, hq, dW0)
+        dhq = _linear_dgrad(du, w0)
+        return dhq, dW0, db0, dW2, db2, None
+
+
+def layer_params(layer):
+    """The 12 parameter tensors of one nn.TransformerEncoderLayer in LAYER_PARAM_NAMES order."""
+    return (layer.self_attn.in_proj_weight, layer.self_attn.in_proj_bias, layer.self_attn.out_proj.weight,
+            layer.self_attn.out_proj.bias, layer.linear1.weight, layer.linear1.bias, layer.linear2.weight,
+            layer.linear2.bias, layer.norm1.weight, layer.norm1.bias, layer.norm2.weight, layer.norm2.bias)

@@ -1,0 +1,156 @@
+"""Drop-in `train.train` (reference train.py:22-135) on the sm_100a engine.
+
+Same signature, defaults, prints and return value `(total_loss, positional_losses, model_on_cpu)`.  Differences that
+do not change results: the model forward/backward and the criterion run on hand-written CUDA kernels; the mask is
+never built; per-step `.item()` syncs are replaced by on-device accumulation read once per epoch; under torchrun
+(WORLD_SIZE > 1) `batch_size` is the GLOBAL batch, sharded over ranks with one gradient all-reduce per optimizer
+step (parallel.py).
+"""
+import time
+
+import torch
+from torch import nn
+
+from . import encoders, positional_encodings, parallel
+from .bar_distribution import BarDistribution, FullSupportBarDistribution, get_bucket_limits  # noqa: F401
+from .transformer import TransformerModel
+from .utils import (get_cosine_schedule_with_warmup, get_openai_lr, StoreDictKeyPair,  # noqa: F401
+                    get_weighted_single_eval_pos_sampler, get_uniform_single_eval_pos_sampler)
+
+
+class Losses():
+    gaussian = nn.GaussianNLLLoss(full=True, reduction='none')
+    mse = nn.MSELoss(reduction='none')
+    ce = nn.CrossEntropyLoss(reduction='none')
+    bce = nn.BCEWithLogitsLoss(reduction='none')
+    get_BarDistribution = BarDistribution
+
+
+def _is_bar(criterion):
+    return isinstance(criterion, BarDistribution) or "BarDistribution" in criterion.__class__.__name__
+
+
+def train(priordataloader_class, criterion, encoder_generator, emsize=200, nhid=200, nlayers=6, nhead=2, dropout=0.2,
+          epochs=10, steps_per_epoch=100, batch_size=200, bptt=10, lr=None, warmup_epochs=10, input_normalization=False,
+          y_encoder_generator=None, pos_encoder_generator=None, decoder=None, extra_prior_kwargs_dict={},
+          scheduler=get_cosine_schedule_with_warmup, load_weights_from_this_state_dict=None, validation_period=10,
+          single_eval_pos_gen=None, gpu_device='cuda:0', aggregate_k_gradients=1, verbose=True):
+    world = parallel.world_size()
+    if world > 1 and torch.cuda.is_available():
+        gpu_device = f'cuda:{torch.cuda.current_device()}'
+    device = gpu_device if torch.cuda.is_available() else 'cpu:0'
+    print(f'Using {device} device')
+    assert batch_size % world == 0, f'global batch {batch_size} must be divisible by the world size {world}'
+    local_batch = batch_size // world
+    dl = priordataloader_class(num_steps=steps_per_epoch, batch_size=local_batch, seq_len=bptt, **extra_prior_kwargs_dict)
+
+    encoder = encoder_generator(dl.num_features + 1 if dl.fuse_x_y else dl.num_features, emsize)
+    n_out = dl.num_outputs
+    if isinstance(criterion, nn.GaussianNLLLoss):
+        n_out *= 2
+    elif _is_bar(criterion):
+        assert n_out == 1
+        n_out = criterion.num_bars
+    model = TransformerModel(encoder, n_out, emsize, nhead, nhid, nlayers, dropout,
+                             y_encoder=y_encoder_generator(1, emsize), input_normalization=input_normalization,
+                             pos_encoder=(pos_encoder_generator or positional_encodings.NoPositionalEncoding)(emsize, bptt * 2),
+                             decoder=decoder)
+    model.criterion = criterion
+    if load_weights_from_this_state_dict is not None:
+        model.load_state_dict(load_weights_from_this_state_dict)
+    model.to(device)
+    parallel.broadcast_parameters(model)
+
+    if lr is None:
+        lr = get_openai_lr(model)
+        print(f"Using OpenAI max lr of {lr}.")
+    on_cuda = torch.device(device).type == 'cuda'
+    optimizer = torch.optim.Adam(model.parameters(), lr=lr, **({'fused': True} if on_cuda else {}))
+    scheduler = scheduler(optimizer, warmup_epochs, epochs)
+    params = [p for p in model.parameters() if p.requires_grad]
+
+    def train_epoch():
+        model.train()
+        total_loss = torch.zeros((), device=device)
+        pos_loss = torch.zeros(bptt, device=device)
+        pos_count = torch.zeros(bptt, device=device)
+        before_get_batch = time.time()
+        assert len(dl) % aggregate_k_gradients == 0, \
+            'Please set the number of steps per epoch s.t. `aggregate_k_gradients` divides it.'
+        # one single_eval_pos per global step, identical on every rank (reference train.py:69)
+        seps = [single_eval_pos_gen() if callable(single_eval_pos_gen) else single_eval_pos_gen for _ in range(len(dl))]
+        seps = parallel.broadcast_object(seps)
+        time_to_get_batch = forward_time = step_time = 0.
+        for batch, (data, targets) in enumerate(dl):
+            time_to_get_batch = time.time() - before_get_batch
+            before_forward = time.time()
+            single_eval_pos = seps[batch]
+            data = tuple(e.to(device) for e in data) if isinstance(data, tuple) else data.to(device)
+            output = model(data, single_eval_pos=single_eval_pos)
+            forward_time = time.time() - before_forward
+
+            if single_eval_pos is not None:
+                targets = targets[single_eval_pos:]
+            if isinstance(criterion, nn.GaussianNLLLoss):
+                assert output.shape[-1] == 2, \
+                    'need to write a little bit of code to handle multiple regression targets at once'
+                mean_pred = output[..., 0]
+                var_pred = output[..., 1].abs()
+                losses = criterion(mean_pred.flatten(), targets.to(device).flatten(), var=var_pred.flatten())
+            elif isinstance(criterion, (nn.MSELoss, nn.BCEWithLogitsLoss)):
+                losses = criterion(output.flatten(), targets.to(device).flatten())
+            else:
+                losses = criterion(output.reshape(-1, n_out), targets.to(device).flatten())
+            losses = losses.view(*output.shape[0:2]).squeeze(-1)
+
+            loss = losses.mean()
+            loss.backward()
+            if batch % aggregate_k_gradients == aggregate_k_gradients - 1:
+                parallel.allreduce_gradients(params)
+                torch.nn.utils.clip_grad_norm_(model.parameters(), 1.)
+                optimizer.step()
+                optimizer.zero_grad()
+            step_time = time.time() - before_forward
+
+            ld = loss.detach()
+            total_loss += ld
+            if single_eval_pos is None:
+                pos_loss += losses.mean(1).detach()
+                pos_count += 1
+            else:
+                pos_loss[single_eval_pos] += ld
+                pos_count[single_eval_pos] += 1
+            before_get_batch = time.time()
+
+        if _is_bar(criterion) and hasattr(criterion, 'check_support'):
+            criterion.check_support()
+        total_loss = parallel.allreduce_mean_scalar(total_loss)
+        pos_loss = parallel.allreduce_mean_scalar(pos_loss)
+        return (total_loss.item() / steps_per_epoch, (pos_loss / pos_count).tolist(), time_to_get_batch, forward_time,
+                step_time)
+
+    total_loss = float('inf')
+    total_positional_losses = float('inf')
+    prev_defer = BarDistribution.defer_support_check
+    BarDistribution.defer_support_check = True
+    try:
+        for epoch in range(1, epochs + 1):
+            epoch_start_time = time.time()
+            total_loss, total_positional_losses, time_to_get_batch, forward_time, step_time = train_epoch()
+            if hasattr(dl, 'validate') and epoch % validation_period == 0:
+                with torch.no_grad():
+                    val_score = dl.validate(model)
+            else:
+                val_score = None
+            if verbose:
+                print('-' * 89)
+                print(
+                    f'| end of epoch {epoch:3d} | time: {(time.time() - epoch_start_time):5.2f}s | mean loss {total_loss:5.2f} | '
+                    f"pos losses {','.join([f'{l:5.2f}' for l in total_positional_losses])}, lr {scheduler.get_last_lr()[0]}"
+                    f' data time {time_to_get_batch:5.2f} step time {step_time:5.2f}'
+                    f' forward time {forward_time:5.2f}' + (f'val score {val_score}' if val_score is not None else ''))
+                print('-' * 89)
+            scheduler.step()
+    finally:
+        BarDistribution.defer_support_check = prev_defer
+    return total_loss, total_positional_losses, model.to('cpu')
