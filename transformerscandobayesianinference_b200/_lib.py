@@ -55,6 +55,22 @@ EXPORTED_SYMBOLS = [
 ]
 
 _lib = None
+_launches = 0          # kernel launches issued through this binding (bench.py reports it as gpu_launches)
+PROFILE_GEMM = None    # when a list: (flops, start_event, end_event) is appended for every tcgen05 GEMM launch
+
+
+def reset_launch_count():
+    global _launches
+    _launches = 0
+
+
+def launch_count():
+    return _launches
+
+
+def _count(n=1):
+    global _launches
+    _launches += n
 
 
 def load():
@@ -151,8 +167,16 @@ def gemm(A, B, C, *, a_mn_major=False, b_mn_major=False, bias=None, aux=None, C2
     d.ab_dtype = dtype_code(A)
     if use_tc is None:
         use_tc = tc_gemm_ok(A, B, C, aux, C2)
+    _count()
     if use_tc:
-        check(lib.pfn_gemm_bf16_tc(ctypes.byref(d), stream_ptr()), "pfn_gemm_bf16_tc")
+        if PROFILE_GEMM is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            check(lib.pfn_gemm_bf16_tc(ctypes.byref(d), stream_ptr()), "pfn_gemm_bf16_tc")
+            e1.record()
+            PROFILE_GEMM.append((2.0 * M * N * K, e0, e1))
+        else:
+            check(lib.pfn_gemm_bf16_tc(ctypes.byref(d), stream_ptr()), "pfn_gemm_bf16_tc")
     else:
         check(lib.pfn_gemm_simt(ctypes.byref(d), stream_ptr()), "pfn_gemm_simt")
 
@@ -187,6 +211,7 @@ def tc_attention_ok(qkv, dh, T=None):
 
 
 def attention_fwd(qkv, out, lse, T, B, H, dh, sep, use_tc=None):
+    _count(1)
     lib = load()
     require_cuda(qkv, out, lse)
     d = attention_desc(qkv, out, lse, T, B, H, dh, sep)
@@ -197,6 +222,7 @@ def attention_fwd(qkv, out, lse, T, B, H, dh, sep, use_tc=None):
 
 
 def attention_bwd(qkv, out, lse, dout, dqkv, delta, T, B, H, dh, sep, use_tc=None):
+    _count(2)
     lib = load()
     require_cuda(qkv, out, lse, dout, dqkv, delta)
     d = attention_desc(qkv, out, lse, T, B, H, dh, sep, dout, dqkv, delta)
@@ -207,18 +233,21 @@ def attention_bwd(qkv, out, lse, dout, dqkv, delta, T, B, H, dh, sep, use_tc=Non
 
 
 def embed_fwd(x, y, Wx, bx, wy, by, out, T, B, F, E, sep):
+    _count(1)
     require_cuda(x, y, Wx, bx, wy, by, out)
     check(load().pfn_embed_fwd(ptr(x), ptr(y), ptr(Wx), ptr(bx), ptr(wy), ptr(by), ptr(out), dtype_code(out), T, B, F,
                                E, sep, stream_ptr()), "pfn_embed_fwd")
 
 
 def embed_bwd(dout, x, y, dWx, dbx, dwy, dby, T, B, F, E, sep):
+    _count((F + 7) // 8)
     require_cuda(dout, x, y, dWx, dbx, dwy, dby)
     check(load().pfn_embed_bwd(ptr(dout), dtype_code(dout), ptr(x), ptr(y), ptr(dWx), ptr(dbx), ptr(dwy), ptr(dby), T,
                                B, F, E, sep, stream_ptr()), "pfn_embed_bwd")
 
 
 def layernorm_fwd(z, gamma, beta, h, mean, rstd, eps=1e-5):
+    _count(1)
     require_cuda(z, gamma, beta, h, mean, rstd)
     rows, E = z.shape
     check(load().pfn_layernorm_fwd(ptr(z), z.stride(0), ptr(gamma), ptr(beta), ptr(h), h.stride(0), ptr(mean),
@@ -226,6 +255,7 @@ def layernorm_fwd(z, gamma, beta, h, mean, rstd, eps=1e-5):
 
 
 def layernorm_bwd(dh, z, mean, rstd, gamma, dz, dgamma, dbeta, colsum_out=None):
+    _count(1)
     require_cuda(dh, z, mean, rstd, gamma, dz, dgamma, dbeta, colsum_out)
     rows, E = z.shape
     check(load().pfn_layernorm_bwd(ptr(dh), dh.stride(0), ptr(z), z.stride(0), ptr(mean), ptr(rstd), ptr(gamma),
@@ -234,6 +264,7 @@ def layernorm_bwd(dh, z, mean, rstd, gamma, dz, dgamma, dbeta, colsum_out=None):
 
 
 def colsum(X, out, N=None):
+    _count(1)
     require_cuda(X, out)
     rows = X.shape[0]
     N = X.shape[1] if N is None else N
@@ -241,6 +272,7 @@ def colsum(X, out, N=None):
 
 
 def bar_nll_fwd(logits, y, borders, n_bars, full_support, nll, idx, lse, oob_count):
+    _count(1)
     require_cuda(logits, y, borders, nll, idx, lse, oob_count)
     rows = logits.shape[0]
     check(load().pfn_bar_nll_fwd(ptr(logits), logits.stride(0), dtype_code(logits), ptr(y), ptr(borders), n_bars,
@@ -249,6 +281,7 @@ def bar_nll_fwd(logits, y, borders, n_bars, full_support, nll, idx, lse, oob_cou
 
 
 def bar_nll_bwd(logits, idx, lse, g, dlogits, n_bars, n_cols_pad=None):
+    _count(1)
     require_cuda(logits, idx, lse, g, dlogits)
     rows = logits.shape[0]
     n_cols_pad = n_bars if n_cols_pad is None else n_cols_pad
@@ -258,12 +291,14 @@ def bar_nll_bwd(logits, idx, lse, g, dlogits, n_bars, n_cols_pad=None):
 
 
 def bar_bucket_idx(y, borders, n_bars, idx):
+    _count(1)
     require_cuda(y, borders, idx)
     check(load().pfn_bar_bucket_idx(ptr(y), ptr(borders), n_bars, ptr(idx), y.numel(), stream_ptr()),
           "pfn_bar_bucket_idx")
 
 
 def gp_sample(x, z, ls, os_, noise, jitter, kernel_type, y, work, info):
+    _count(1)
     require_cuda(x, z, ls, os_, noise, y, work, info)
     Bn, T, F = x.shape
     check(load().pfn_gp_sample(ptr(x), ptr(z), ptr(ls), ptr(os_), ptr(noise), float(jitter), int(kernel_type), ptr(y),

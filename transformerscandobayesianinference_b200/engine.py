@@ -83,7 +83,7 @@ class EncoderStackFn(torch.autograd.Function):
         n_layers = len(params) // N_LAYER_PARAMS
         N, E = src.shape
         dh = E // nhead
-        keep = torch.is_grad_enabled() and (src.requires_grad or any(p.requires_grad for p in params))
+        keep = any(ctx.needs_input_grad)   # grad mode is off inside Function.forward; this reflects the caller's mode
         saved = []
         h = src.contiguous()
         for li in range(n_layers):
