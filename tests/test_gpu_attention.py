@@ -71,3 +71,26 @@ def test_attention_tc_large_scores_rescale(cuda_device):
     ref, ref_lse = O.attention_ref(qkv.float().cpu().double(), T, B, H, dh, sep)
     assert (out.float().cpu().double() - ref).abs().max().item() <= 3e-2 * ref.abs().max().item()
     assert (lse.cpu().double() - ref_lse).abs().max().item() <= 2e-3 * (ref_lse.abs().max().item() + 1)
+
+
+@pytest.mark.parametrize("T,B,H,sep", TC_CASES + [(1000, 1, 2, 1000), (96, 1, 1, 33)])
+def test_attention_tc_bwd(cuda_device, T, B, H, sep):
+    torch.manual_seed(T * 3 + sep)
+    dh = 128
+    E = H * dh
+    qkv = (torch.randn(T * B, 3 * E, device=cuda_device) * 1.2).to(torch.bfloat16)
+    out, lse = _run_fwd(qkv, T, B, H, dh, sep, use_tc=True)
+    dout = torch.randn(T * B, E, device=cuda_device).to(torch.bfloat16)
+    dqkv = torch.full_like(qkv, float("nan"))
+    delta = torch.empty(B * H, T, device=cuda_device)
+    L.attention_bwd(qkv, out, lse, dout, dqkv, delta, T, B, H, dh, sep, use_tc=True)
+    torch.cuda.synchronize()
+    qr = qkv.float().cpu().double().requires_grad_(True)
+    ref, _ = O.attention_ref(qr, T, B, H, dh, sep)
+    (ref * dout.float().cpu().double()).sum().backward()
+    got = dqkv.float().cpu().double()
+    assert torch.isfinite(got).all(), "dqkv not fully written"
+    for name, sl in (("dq", slice(0, E)), ("dk", slice(E, 2 * E)), ("dv", slice(2 * E, 3 * E))):
+        want = qr.grad[:, sl]
+        err = (got[:, sl] - want).abs().max().item()
+        assert err <= 3e-2 * (want.abs().max().item() + 1e-6), f"{name}: err {err} vs scale {want.abs().max().item()}"

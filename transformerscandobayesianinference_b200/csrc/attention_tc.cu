@@ -388,9 +388,3 @@ extern "C" int pfn_attention_fwd_tc(const pfn_attn_desc* d, void* stream) {
   PFN_LAUNCH_OK();
   return 0;
 }
-
-extern "C" int pfn_attention_bwd_tc(const pfn_attn_desc* d, void* stream) {
-  (void)d; (void)stream;
-  set_error("attention_bwd_tc: not built in this revision (use pfn_attention_bwd_simt)");
-  return 4;
-}

@@ -24,6 +24,7 @@ SOURCES = [
     "bar_nll.cu",
     "attention_simt.cu",
     "attention_tc.cu",
+    "attention_bwd_tc.cu",
     "gp_sampler.cu",
 ]
 

@@ -152,7 +152,7 @@ class EncoderStackFn(torch.autograd.Function):
             dattn = _linear_dgrad(dz1, out_w)
             dqkv = torch.empty_like(qkv)
             delta = torch.empty_like(lse)
-            L.attention_bwd(qkv, attn, lse, dattn, dqkv, delta, T, B, nhead, dh, sep, use_tc=False)
+            L.attention_bwd(qkv, attn, lse, dattn, dqkv, delta, T, B, nhead, dh, sep)
             del dattn, attn, qkv
             L.colsum(dqkv, G["in_b"])
             _linear_wgrad(dqkv, h, G["in_w"])
