@@ -96,7 +96,7 @@ def run_reference(args):
         return
     from oracle import cpu_reference_step as C
     cfg = CFG2
-    threads = os.cpu_count() or 1
+    threads = cpu_threads()
     torch.set_num_threads(threads)
     sample_b = args.ref_batch
     borders = torch.linspace(-4.0, 4.0, cfg["n_bars"] + 1)
@@ -114,6 +114,12 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "seq/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def cpu_threads():
+    """Threads for the CPU arm: torch's intra-op pool scales poorly past a few dozen threads on this small per-step
+    problem (128 threads measured 40x slower than 8), so use at most 32 and report the number actually used."""
+    return max(1, min(os.cpu_count() or 1, int(os.environ.get("PFN_CPU_THREADS", "32"))))
 
 
 def workload_name(cfg, batch):
@@ -237,7 +243,7 @@ def run_engine(args):
     cpu_baseline = None
     if not args.no_cpu_baseline:
         from oracle import cpu_reference_step as C
-        threads = os.cpu_count() or 1
+        threads = cpu_threads()
         cb = args.ref_batch
         stepc, _ = C.make_step(T, F, E, H, nhid, Lyr, n_bars, sep, cb, cfg["hps"], borders, threads)
         dtc = C.time_steps(stepc, 3, 1)

@@ -281,6 +281,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
           tc::tmem_st_32x32b_x16(tmem_base + lane_off + buf * 64 + half * 16, pk);
         }
         tc::tmem_st_wait();
+        // observe every dq_done phase in order (see attention_tc.cu: parity waits must not run two phases ahead)
+        if (j > 0) tc::mbar_wait(dq_done, (g - 1) & 1);
         tc::tc_fence_before();
         tc::mbar_arrive(&ds_ready[buf]);
       }
@@ -505,6 +507,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
           tc::tmem_st_32x32b_x16(tmem_base + lane_off + 128 + buf * 64 + half * 16, pkd);
         }
         tc::tmem_st_wait();
+        if (i > 0) tc::mbar_wait(acc_done, (g - 1) & 1);   // keep in step with every acc_done phase
         tc::tc_fence_before();
         tc::mbar_arrive(&pds_ready[buf]);
       }

@@ -247,14 +247,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         bm *= p.scale_log2;
         const bool need = bm > m + kRescaleThreshold;   // also true when m == -inf
+        // Observe EVERY pv_done phase in order (a parity wait that runs two phases ahead of the barrier would pass
+        // spuriously): block g-1's P V must be complete before O may be rescaled and before P_g is published.
+        if (j > 0) {
+          tc::mbar_wait(pv_done, (g - 1) & 1);
+          tc::tc_fence_after();
+        }
         if (__any_sync(0xffffffffu, need)) {
           const float m_new = need ? bm : m;
           const float factor = need ? tc::fast_exp2(m - m_new) : 1.0f;   // exp2(-inf) = 0
           l *= factor;
           m = m_new;
           if (j > 0) {
-            tc::mbar_wait(pv_done, (g - 1) & 1);
-            tc::tc_fence_after();
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
               uint32_t o[32];
