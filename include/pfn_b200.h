@@ -80,12 +80,15 @@ typedef struct pfn_attn_desc {
   const void* dout; int ld_dout;
   void* dqkv; int ld_dqkv;
   float* delta;            /* [B*H, T] fp32 scratch for backward: rowsum(dO * O) */
+  int batch_major;         /* 0: token row = t*B + b (reference layout); 1: token row = b*T + t (tcgen05 kernels only) */
 } pfn_attn_desc;
 
 int pfn_attention_fwd_simt(const pfn_attn_desc* d, void* stream);
 int pfn_attention_bwd_simt(const pfn_attn_desc* d, void* stream);
 int pfn_attention_fwd_tc(const pfn_attn_desc* d, void* stream);
 int pfn_attention_bwd_tc(const pfn_attn_desc* d, void* stream);
+/* debug: clock64 event log of CTA 0 of subsequent pfn_attention_fwd_tc launches ([1 + 4*cap] int64; null = off) */
+int pfn_debug_attention_trace(long long* buf, int cap);
 
 /* ------------------------------------------------------------------------------------------------
  * Embedding stage (reference transformer.py:68-74):

@@ -93,4 +93,5 @@ def test_attention_tc_bwd(cuda_device, T, B, H, sep):
     for name, sl in (("dq", slice(0, E)), ("dk", slice(E, 2 * E)), ("dv", slice(2 * E, 3 * E))):
         want = qr.grad[:, sl]
         err = (got[:, sl] - want).abs().max().item()
-        assert err <= 3e-2 * (want.abs().max().item() + 1e-6), f"{name}: err {err} vs scale {want.abs().max().item()}"
+        scale_all = qr.grad.abs().max().item()
+        assert err <= 3e-2 * want.abs().max().item() + 1e-3 * scale_all, f"{name}: err {err} vs scale {want.abs().max().item()}"

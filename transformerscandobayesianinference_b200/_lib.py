@@ -40,7 +40,7 @@ class AttnDesc(ctypes.Structure):
         ("lse", c_void_p),
         ("dout", c_void_p), ("ld_dout", c_int),
         ("dqkv", c_void_p), ("ld_dqkv", c_int),
-        ("delta", c_void_p),
+        ("delta", c_void_p), ("batch_major", c_int),
     ]
 
 
@@ -48,6 +48,7 @@ EXPORTED_SYMBOLS = [
     "pfn_last_error", "pfn_version", "pfn_num_sms",
     "pfn_gemm_bf16_tc", "pfn_gemm_simt",
     "pfn_attention_fwd_simt", "pfn_attention_bwd_simt", "pfn_attention_fwd_tc", "pfn_attention_bwd_tc",
+    "pfn_debug_attention_trace",
     "pfn_embed_fwd", "pfn_embed_bwd",
     "pfn_layernorm_fwd", "pfn_layernorm_bwd", "pfn_colsum",
     "pfn_bar_nll_fwd", "pfn_bar_nll_bwd", "pfn_bar_bucket_idx",
@@ -93,6 +94,7 @@ def load():
     lib.pfn_gemm_simt.argtypes = [ctypes.POINTER(GemmDesc), c_void_p]
     for n in ("pfn_attention_fwd_simt", "pfn_attention_bwd_simt", "pfn_attention_fwd_tc", "pfn_attention_bwd_tc"):
         getattr(lib, n).argtypes = [ctypes.POINTER(AttnDesc), c_void_p]
+    lib.pfn_debug_attention_trace.argtypes = [c_void_p, c_int]
     lib.pfn_embed_fwd.argtypes = [c_void_p] * 7 + [c_int] * 6 + [c_void_p]
     lib.pfn_embed_bwd.argtypes = [c_void_p, c_int] + [c_void_p] * 6 + [c_int] * 5 + [c_void_p]
     lib.pfn_layernorm_fwd.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
@@ -191,8 +193,9 @@ def tc_gemm_ok(A, B, C, aux=None, C2=None):
     return C.stride(0) % cmul == 0 and C.data_ptr() % 16 == 0
 
 
-def attention_desc(qkv, out, lse, T, B, H, dh, sep, dout=None, dqkv=None, delta=None):
+def attention_desc(qkv, out, lse, T, B, H, dh, sep, dout=None, dqkv=None, delta=None, batch_major=False):
     d = AttnDesc()
+    d.batch_major = int(batch_major)
     d.T, d.B, d.H, d.dh, d.sep = T, B, H, dh, sep
     d.dtype = dtype_code(qkv)
     d.scale = 1.0 / (dh ** 0.5)
@@ -210,22 +213,22 @@ def tc_attention_ok(qkv, dh, T=None):
     return qkv.dtype == torch.bfloat16 and dh == 128 and qkv.stride(0) % 8 == 0 and qkv.data_ptr() % 16 == 0
 
 
-def attention_fwd(qkv, out, lse, T, B, H, dh, sep, use_tc=None):
+def attention_fwd(qkv, out, lse, T, B, H, dh, sep, use_tc=None, batch_major=False):
     _count(1)
     lib = load()
     require_cuda(qkv, out, lse)
-    d = attention_desc(qkv, out, lse, T, B, H, dh, sep)
+    d = attention_desc(qkv, out, lse, T, B, H, dh, sep, batch_major=batch_major)
     if use_tc is None:
         use_tc = tc_attention_ok(qkv, dh)
     fn = lib.pfn_attention_fwd_tc if use_tc else lib.pfn_attention_fwd_simt
     check(fn(ctypes.byref(d), stream_ptr()), "pfn_attention_fwd")
 
 
-def attention_bwd(qkv, out, lse, dout, dqkv, delta, T, B, H, dh, sep, use_tc=None):
+def attention_bwd(qkv, out, lse, dout, dqkv, delta, T, B, H, dh, sep, use_tc=None, batch_major=False):
     _count(2)
     lib = load()
     require_cuda(qkv, out, lse, dout, dqkv, delta)
-    d = attention_desc(qkv, out, lse, T, B, H, dh, sep, dout, dqkv, delta)
+    d = attention_desc(qkv, out, lse, T, B, H, dh, sep, dout, dqkv, delta, batch_major=batch_major)
     if use_tc is None:
         use_tc = tc_attention_ok(qkv, dh)
     fn = lib.pfn_attention_bwd_tc if use_tc else lib.pfn_attention_bwd_simt

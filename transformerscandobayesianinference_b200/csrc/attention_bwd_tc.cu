@@ -1,11 +1,15 @@
-// tcgen05 backward of the single_eval_pos-masked attention (head dim 128, bf16), two kernels:
+// tcgen05 backward of the single_eval_pos-masked attention (head dim 128, bf16), three kernels:
 //
-//  (1) attn_bwd_dq_tc_kernel   one CTA per (batch, head, 128-row query tile), loop over 64-key blocks j < sep:
+//  (0) attn_bwd_delta_kernel   delta[b,h,i] = dO_i . O_i   (one warp per token row, HBM-bound, 16 B vectors)
+//
+//  (1) attn_bwd_dq_tc_kernel   one CTA per (batch, head, 128-row query tile); blocks = 64-key blocks of the train keys
+//      followed by up to two "diagonal" blocks (the tile's own rows as keys; row i keeps only key i, cf. attention_tc.cu):
 //          S_j  = Q K_j^T          dP_j = dO V_j^T                      (SS MMAs, 128x64x128, TMEM double-buffered)
 //          dS_j = exp2(S_j c - lse) * (dP_j - delta) * scale   -> bf16 -> TMEM   (one thread per query row)
 //          dQ  += dS_j K_j                                                (TS MMA, K_j read MN-major from the same smem)
-//      plus, per row, delta_i = dO_i . O_i (stored for kernel 2) and the diagonal key of a query row (i >= sep):
-//      its dq contribution and — since nobody else attends to that key — the complete dK_i, dV_i.
+//      For a query row the diagonal key is attended by that row only, so dK_i = dS_ii q_i and dV_i = P_ii dO_i are
+//      complete: the owning thread scales its own q / dO row (read back from the swizzled smem tiles) and stores them.
+//      Q and dO tiles are double-buffered so the next tile's loads overlap this tile's epilogue.
 //
 //  (2) attn_bwd_dkv_tc_kernel  one CTA per (batch, head, 128-key tile of the train keys), loop over 64-row blocks i:
 //          S^T_i = K Q_i^T         dP^T_i = V dO_i^T                      (lane = key, column = query row)
@@ -24,10 +28,12 @@ namespace pfn {
 int check_attn_desc_public(const pfn_attn_desc* d, bool bwd, const char* who);
 
 constexpr int AB_DH = 128;
-constexpr int AB_THREADS = 192;
+constexpr int AB_THREADS = 320;                   // warp 0 TMA, warp 1 MMA, warps 2..9 elementwise (2 per TMEM lane quarter)
+constexpr int AB_EW_THREADS = 256;
 constexpr int AB_TILE_BYTES = 128 * AB_DH * 2;     // 32 KB : 128-row operand tile (2 chunks of 16 KB)
 constexpr int AB_BLK_BYTES = 64 * AB_DH * 2;       // 16 KB : 64-row operand block (2 chunks of 8 KB)
-constexpr int AB_SMEM = 2 * AB_TILE_BYTES + 2 * 2 * AB_BLK_BYTES + 1024 /*lse/delta*/ + 256 + 1024;
+constexpr int AB_KS = 4;                           // depth of the 64-row block ring (TMA runs 3 blocks ahead of the MMAs)
+constexpr int AB_SMEM = 2 * AB_TILE_BYTES + AB_KS * 2 * AB_BLK_BYTES + 1024 /*lse/delta*/ + 256 + 1024;   // both kernels                      // dQ kernel
 
 struct AttnBwdParams {
   int T, B, H, sep;
@@ -40,6 +46,7 @@ struct AttnBwdParams {
   float* delta;
   int n_tiles;
   int total_work;
+  int batch_major;
 };
 
 __device__ __forceinline__ void ab_load32(const __nv_bfloat16* p, float (&v)[32]) {
@@ -107,7 +114,73 @@ __device__ __forceinline__ void ab_mma_ts_128x128(uint32_t d_tmem, uint32_t a_tm
 }
 
 // =====================================================================================================================
-// Kernel 1: dQ (+ delta, + diagonal-key dK/dV of query rows)
+// Kernel 0: delta = rowsum(dO * O) per (batch, head, row)
+// =====================================================================================================================
+__global__ void __launch_bounds__(256)
+attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ out, int ld_out, const __nv_bfloat16* __restrict__ dout,
+                      int ld_dout, float* __restrict__ delta, int T, int B, int H, int batch_major) {
+  // one warp per token; a 128-wide head = 16 lanes x 8 elements, so a warp covers two heads per pass
+  const int lane = threadIdx.x & 31;
+  const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const long long rows = static_cast<long long>(T) * B;
+  for (long long tok = warp; tok < rows; tok += nwarps) {
+    const int t = batch_major ? static_cast<int>(tok % T) : static_cast<int>(tok / B);
+    const int b = batch_major ? static_cast<int>(tok / T) : static_cast<int>(tok % B);
+    for (int h0 = 0; h0 < H; h0 += 2) {
+      const int h = h0 + (lane >> 4);
+      float acc = 0.f;
+      if (h < H) {
+        const int col = h * AB_DH + (lane & 15) * 8;
+        const uint4 pa = *reinterpret_cast<const uint4*>(out + tok * ld_out + col);
+        const uint4 pb = *reinterpret_cast<const uint4*>(dout + tok * ld_dout + col);
+        const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&pa);
+        const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&pb);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 x = __bfloat1622float2(ha[j]);
+          const float2 y = __bfloat1622float2(hb[j]);
+          acc = fmaf(x.x, y.x, acc);
+          acc = fmaf(x.y, y.y, acc);
+        }
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if ((lane & 15) == 0 && h < H) delta[(static_cast<size_t>(b) * H + h) * T + t] = acc;
+    }
+  }
+}
+
+__device__ __forceinline__ int ab_tile_block_plan(int i0, int sep, int T, int nblk, int (&dstart)[2]) {
+  int nd = 0;
+#pragma unroll
+  for (int jj = 0; jj < 2; ++jj) {
+    const int lo = i0 + 64 * jj;
+    if (lo < T && lo + 63 >= sep) dstart[nd++] = lo;
+  }
+  return nblk + nd;
+}
+
+// 32 consecutive elements (columns c0..c0+31) of row r of a [128 x 128] bf16 tile stored as two 64-column chunks with
+// the TMA 128-byte swizzle (16-byte unit u of a row sits at position u ^ (r & 7)).  Conflict-free for one row per lane.
+__device__ __forceinline__ void ab_load32_swz(const uint8_t* tile, int r, int c0, float (&v)[32]) {
+  const uint8_t* base = tile + (c0 >> 6) * 16384 + r * 128;
+  const int u0 = (c0 & 63) >> 3;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint4 pk = *reinterpret_cast<const uint4*>(base + (((u0 + q) ^ (r & 7)) << 4));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 t = __bfloat1622float2(h[j]);
+      v[q * 8 + 2 * j] = t.x;
+      v[q * 8 + 2 * j + 1] = t.y;
+    }
+  }
+}
+
+// =====================================================================================================================
+// Kernel 1: dQ (+ diagonal-key dK/dV of query rows)
 // =====================================================================================================================
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
@@ -117,16 +190,16 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
   uint8_t* sQ = smem;
   uint8_t* sDO = smem + AB_TILE_BYTES;
   uint8_t* sKV = smem + 2 * AB_TILE_BYTES;               // stage s: K at +s*32K, V at +16K
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * AB_TILE_BYTES + 4 * AB_BLK_BYTES + 1024);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * AB_TILE_BYTES + AB_KS * 2 * AB_BLK_BYTES + 1024);
   uint64_t* qdo_full = bars + 0;
-  uint64_t* qdo_empty = bars + 1;
-  uint64_t* kv_full = bars + 2;     // [2]
-  uint64_t* kv_empty = bars + 4;    // [2]
-  uint64_t* s_full = bars + 6;      // [2]
-  uint64_t* ds_ready = bars + 8;    // [2]
-  uint64_t* dq_done = bars + 10;
-  uint64_t* dq_empty = bars + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* qdo_empty = bars + 1;   // MMA commit after the tile's last score MMA + one arrival per row thread
+  uint64_t* kv_full = bars + 2;     // [AB_KS]
+  uint64_t* kv_empty = bars + 6;    // [AB_KS]
+  uint64_t* s_full = bars + 10;     // [2]
+  uint64_t* ds_ready = bars + 12;   // [2]
+  uint64_t* dq_done = bars + 14;
+  uint64_t* dq_empty = bars + 15;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -139,15 +212,17 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
   }
   if (warp == 1 && lane == 0) {
     tc::mbar_init(qdo_full, 1);
-    tc::mbar_init(qdo_empty, 1);
-    for (int s = 0; s < 2; ++s) {
+    tc::mbar_init(qdo_empty, 1 + AB_EW_THREADS);   // MMA commit (score MMAs done) + every row thread (smem row reads done)
+    for (int s = 0; s < AB_KS; ++s) {
       tc::mbar_init(&kv_full[s], 1);
       tc::mbar_init(&kv_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&s_full[s], 1);
-      tc::mbar_init(&ds_ready[s], 128);
+      tc::mbar_init(&ds_ready[s], AB_EW_THREADS);
     }
     tc::mbar_init(dq_done, 1);
-    tc::mbar_init(dq_empty, 128);
+    tc::mbar_init(dq_empty, AB_EW_THREADS);
     tc::mbar_fence_init();
   }
   if (warp == 2) {
@@ -162,26 +237,28 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
   // TMEM columns: S[2] @0,64 | dP[2] @128,192 | dQ @256..383
 
   if (warp == 0) {
-    if (lane == 0 && nblk > 0) {
+    if (lane == 0) {
       uint32_t g = 0, tcount = 0;
       for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
         const int bh = w / p.n_tiles;
         const int qt = w - bh * p.n_tiles;
         const int b = bh / p.H, h = bh - b * p.H;
         const int i0 = qt * 128;
+        int dstart[2];
+        const int nb = ab_tile_block_plan(i0, p.sep, p.T, nblk, dstart);
         tc::mbar_wait(qdo_empty, (tcount & 1) ^ 1);
         tc::mbar_expect_tx(qdo_full, 2 * AB_TILE_BYTES);
         tc::tma_load_3d(sQ, &tmQKV128, qdo_full, h * AB_DH, b, i0);
         tc::tma_load_3d(sQ + 16384, &tmQKV128, qdo_full, h * AB_DH + 64, b, i0);
         tc::tma_load_3d(sDO, &tmDO128, qdo_full, h * AB_DH, b, i0);
         tc::tma_load_3d(sDO + 16384, &tmDO128, qdo_full, h * AB_DH + 64, b, i0);
-        for (int j = 0; j < nblk; ++j, ++g) {
-          const int st = g & 1;
-          tc::mbar_wait(&kv_empty[st], ((g >> 1) & 1) ^ 1);
+        for (int j = 0; j < nb; ++j, ++g) {
+          const int st = g % AB_KS;
+          tc::mbar_wait(&kv_empty[st], ((g / AB_KS) & 1) ^ 1);
           tc::mbar_expect_tx(&kv_full[st], 2 * AB_BLK_BYTES);
           uint8_t* kdst = sKV + st * 2 * AB_BLK_BYTES;
           uint8_t* vdst = kdst + AB_BLK_BYTES;
-          const int j0 = j * 64;
+          const int j0 = j < nblk ? j * 64 : dstart[j - nblk];
           tc::tma_load_3d(kdst, &tmQKV64, &kv_full[st], E + h * AB_DH, b, j0);
           tc::tma_load_3d(kdst + 8192, &tmQKV64, &kv_full[st], E + h * AB_DH + 64, b, j0);
           tc::tma_load_3d(vdst, &tmQKV64, &kv_full[st], 2 * E + h * AB_DH, b, j0);
@@ -191,24 +268,27 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0 && nblk > 0) {
-      const uint32_t q_addr = tc::smem_u32(sQ), do_addr = tc::smem_u32(sDO);
+    if (lane == 0) {
       uint32_t g = 0, tcount = 0;
-      auto issue_scores = [&](uint32_t gg) {
-        const uint32_t k_addr = tc::smem_u32(sKV + (gg & 1) * 2 * AB_BLK_BYTES);
-        ab_mma_ss_128x64(tmem_base + (gg & 1) * 64, q_addr, k_addr);                       // S  = Q K^T
-        ab_mma_ss_128x64(tmem_base + 128 + (gg & 1) * 64, do_addr, k_addr + AB_BLK_BYTES); // dP = dO V^T
-      };
       for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
+        const int qt = w % p.n_tiles;
+        int dstart[2];
+        const int nb = ab_tile_block_plan(qt * 128, p.sep, p.T, nblk, dstart);
+        const uint32_t q_addr = tc::smem_u32(sQ), do_addr = tc::smem_u32(sDO);
+        auto issue_scores = [&](uint32_t gg) {
+          const uint32_t k_addr = tc::smem_u32(sKV + (gg % AB_KS) * 2 * AB_BLK_BYTES);
+          ab_mma_ss_128x64(tmem_base + (gg & 1) * 64, q_addr, k_addr);                       // S  = Q K^T
+          ab_mma_ss_128x64(tmem_base + 128 + (gg & 1) * 64, do_addr, k_addr + AB_BLK_BYTES); // dP = dO V^T
+        };
         tc::mbar_wait(qdo_full, tcount & 1);
-        tc::mbar_wait(&kv_full[g & 1], (g >> 1) & 1);
+        tc::mbar_wait(&kv_full[g % AB_KS], (g / AB_KS) & 1);
         tc::tc_fence_after();
         issue_scores(g);
         tc::umma_commit(&s_full[g & 1]);
-        for (int j = 0; j < nblk; ++j, ++g) {
-          if (j + 1 < nblk) {
+        for (int j = 0; j < nb; ++j, ++g) {
+          if (j + 1 < nb) {
             const uint32_t gn = g + 1;
-            tc::mbar_wait(&kv_full[gn & 1], (gn >> 1) & 1);
+            tc::mbar_wait(&kv_full[gn % AB_KS], (gn / AB_KS) & 1);
             tc::tc_fence_after();
             issue_scores(gn);
             tc::umma_commit(&s_full[gn & 1]);
@@ -218,112 +298,127 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
           tc::mbar_wait(&ds_ready[g & 1], (g >> 1) & 1);
           if (j == 0) tc::mbar_wait(dq_empty, (tcount & 1) ^ 1);
           tc::tc_fence_after();
-          const uint32_t k_addr = tc::smem_u32(sKV + (g & 1) * 2 * AB_BLK_BYTES);
+          const uint32_t k_addr = tc::smem_u32(sKV + (g % AB_KS) * 2 * AB_BLK_BYTES);
           ab_mma_ts_128x128(tmem_base + 256, tmem_base + (g & 1) * 64, k_addr, j > 0);     // dQ += dS K
-          tc::umma_commit(&kv_empty[g & 1]);
+          tc::umma_commit(&kv_empty[g % AB_KS]);
           tc::umma_commit(dq_done);
         }
       }
     }
     __syncwarp();
   } else {
-    const int quarter = warp & 3;
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may touch
+    const int half = (warp - 2) >> 2;             // which 32 of a block's 64 key columns this warp owns
     const int row = quarter * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    uint32_t g = 0;
-    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+    uint32_t g = 0, tcount = 0;
+    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
       const int bh = w / p.n_tiles;
       const int qt = w - bh * p.n_tiles;
       const int b = bh / p.H, h = bh - b * p.H;
-      const int i = qt * 128 + row;
+      const int i0 = qt * 128;
+      const int i = i0 + row;
       const bool valid = i < p.T;
       const bool is_query = valid && i >= p.sep;
-      const size_t tok = static_cast<size_t>(valid ? i : 0) * p.B + b;
-      const __nv_bfloat16* qrow = p.qkv + tok * p.ld_qkv + h * AB_DH;
-      const __nv_bfloat16* dorow = p.dout + tok * p.ld_dout + h * AB_DH;
-      float lse2 = INFINITY, delta = 0.f, ds_ii = 0.f, p_ii = 0.f;
+      int dstart[2];
+      const int nb = ab_tile_block_plan(i0, p.sep, p.T, nblk, dstart);
+      tc::mbar_wait(qdo_full, tcount & 1);     // acquire the TMA-written Q / dO tiles (rows are read back in diagonal blocks)
+      float lse2 = INFINITY, dls = 0.f;       // dls = delta * scale
       if (valid) {
         lse2 = p.lse[static_cast<size_t>(bh) * p.T + i] * 1.4426950408889634f;
-        delta = ab_dot128(dorow, p.out + tok * p.ld_out + h * AB_DH);
-        p.delta[static_cast<size_t>(bh) * p.T + i] = delta;
-        if (is_query) {
-          const float s_ii = ab_dot128(qrow, qrow + E);
-          p_ii = tc::fast_exp2(fmaf(s_ii, p.scale_log2, -lse2));
-          const float dp_ii = ab_dot128(dorow, qrow + 2 * E);
-          ds_ii = p_ii * (dp_ii - delta) * p.scale;
-        }
+        dls = p.delta[static_cast<size_t>(bh) * p.T + i] * p.scale;
       }
-      for (int j = 0; j < nblk; ++j, ++g) {
+      for (int j = 0; j < nb; ++j, ++g) {
         const uint32_t buf = g & 1;
         tc::mbar_wait(&s_full[buf], (g >> 1) & 1);
         tc::tc_fence_after();
-        const int kmax = p.sep - j * 64;
+        const bool dense = j < nblk;
+        const int kmax = dense ? p.sep - j * 64 : 0;
+        uint32_t s[32], dp[32], pk[16];
+        tc::tmem_ld_32x32b_x32(tmem_base + lane_off + buf * 64 + half * 32, s);
+        tc::tmem_ld_32x32b_x32(tmem_base + lane_off + 128 + buf * 64 + half * 32, dp);
+        tc::tmem_ld_wait();
+        if (dense && kmax >= 64) {
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t s[32], dp[32], pk[16];
-          tc::tmem_ld_32x32b_x32(tmem_base + lane_off + buf * 64 + half * 32, s);
-          tc::tmem_ld_32x32b_x32(tmem_base + lane_off + 128 + buf * 64 + half * 32, dp);
-          tc::tmem_ld_wait();
+          for (int c = 0; c < 16; ++c) {
+            const float p0 = tc::fast_exp2(fmaf(__uint_as_float(s[2 * c]), p.scale_log2, -lse2));
+            const float p1 = tc::fast_exp2(fmaf(__uint_as_float(s[2 * c + 1]), p.scale_log2, -lse2));
+            pk[c] = tc::pack_bf16x2(p0 * fmaf(__uint_as_float(dp[2 * c]), p.scale, -dls),
+                                    p1 * fmaf(__uint_as_float(dp[2 * c + 1]), p.scale, -dls));
+          }
+        } else if (dense) {
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
             const int k0 = half * 32 + 2 * c;
             float d0 = 0.f, d1 = 0.f;
-            if (k0 < kmax) {
-              const float pr = tc::fast_exp2(fmaf(__uint_as_float(s[2 * c]), p.scale_log2, -lse2));
-              d0 = pr * (__uint_as_float(dp[2 * c]) - delta) * p.scale;
-            }
-            if (k0 + 1 < kmax) {
-              const float pr = tc::fast_exp2(fmaf(__uint_as_float(s[2 * c + 1]), p.scale_log2, -lse2));
-              d1 = pr * (__uint_as_float(dp[2 * c + 1]) - delta) * p.scale;
-            }
+            if (k0 < kmax)
+              d0 = tc::fast_exp2(fmaf(__uint_as_float(s[2 * c]), p.scale_log2, -lse2)) * fmaf(__uint_as_float(dp[2 * c]), p.scale, -dls);
+            if (k0 + 1 < kmax)
+              d1 = tc::fast_exp2(fmaf(__uint_as_float(s[2 * c + 1]), p.scale_log2, -lse2)) * fmaf(__uint_as_float(dp[2 * c + 1]), p.scale, -dls);
             pk[c] = tc::pack_bf16x2(d0, d1);
           }
-          tc::tmem_st_32x32b_x16(tmem_base + lane_off + buf * 64 + half * 16, pk);
+        } else {
+          int cl = -1;                                    // own column inside this warp's half, if any
+          {
+            const int c = i - dstart[j - nblk] - half * 32;
+            if (is_query && c >= 0 && c < 32) cl = c;
+          }
+          float sv = 0.f, dv = 0.f;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            sv = (c == cl) ? __uint_as_float(s[c]) : sv;
+            dv = (c == cl) ? __uint_as_float(dp[c]) : dv;
+          }
+          float dself = 0.f;
+          if (cl >= 0) {
+            // the diagonal key is attended by this row only: dK_i = dS_ii q_i and dV_i = P_ii dO_i are complete.
+            // Q / dO rows are read back from the (still live) swizzled smem tiles.
+            const float pii = tc::fast_exp2(fmaf(sv, p.scale_log2, -lse2));
+            dself = pii * fmaf(dv, p.scale, -dls);
+            const size_t tokq = p.batch_major ? static_cast<size_t>(b) * p.T + i : static_cast<size_t>(i) * p.B + b;
+            __nv_bfloat16* dkv_out = p.dqkv + tokq * p.ld_dqkv + h * AB_DH;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+              float qq[32], dd[32];
+              ab_load32_swz(sQ, row, c * 32, qq);
+              ab_load32_swz(sDO, row, c * 32, dd);
+#pragma unroll
+              for (int e = 0; e < 32; ++e) { qq[e] *= dself; dd[e] *= pii; }
+              ab_store32(dkv_out + E + c * 32, qq);
+              ab_store32(dkv_out + 2 * E + c * 32, dd);
+            }
+          }
+          const uint32_t lo = tc::pack_bf16x2(dself, 0.f), hi = tc::pack_bf16x2(0.f, dself);
+          const int cw = cl >> 1;                         // -1 >> 1 == -1: matches nothing
+          const uint32_t word = (cl & 1) ? hi : lo;
+#pragma unroll
+          for (int c = 0; c < 16; ++c) pk[c] = (c == cw) ? word : 0u;
         }
+        tc::tmem_st_32x32b_x16(tmem_base + lane_off + buf * 64 + half * 16, pk);
         tc::tmem_st_wait();
-        // observe every dq_done phase in order (see attention_tc.cu: parity waits must not run two phases ahead)
-        if (j > 0) tc::mbar_wait(dq_done, (g - 1) & 1);
         tc::tc_fence_before();
         tc::mbar_arrive(&ds_ready[buf]);
       }
-      if (nblk > 0) {
-        tc::mbar_wait(dq_done, (g - 1) & 1);
-        tc::tc_fence_after();
-      }
+      tc::mbar_arrive(qdo_empty);                        // this thread no longer reads the Q / dO tiles
+      // phase-parity safety (see attention_tc.cu): observe dq_done phases g-2 then g-1, in order
+      if (nb >= 2) tc::mbar_wait(dq_done, (g - 2) & 1);
+      tc::mbar_wait(dq_done, (g - 1) & 1);
+      tc::tc_fence_after();
+      const size_t tok = p.batch_major ? static_cast<size_t>(b) * p.T + (valid ? i : 0) : static_cast<size_t>(valid ? i : 0) * p.B + b;
       __nv_bfloat16* dq_out = p.dqkv + tok * p.ld_dqkv + h * AB_DH;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;                      // the pair splits the four 32-column chunks
+        uint32_t raw[32];
         float acc[32];
-        if (nblk > 0) {
-          uint32_t raw[32];
-          tc::tmem_ld_32x32b_x32(tmem_base + lane_off + 256 + c * 32, raw);
-          tc::tmem_ld_wait();
+        tc::tmem_ld_32x32b_x32(tmem_base + lane_off + 256 + c * 32, raw);
+        tc::tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 32; ++e) acc[e] = __uint_as_float(raw[e]);
-        } else {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) acc[e] = 0.f;
-        }
-        if (is_query) {
-          float kk[32], qq[32], dd[32];
-          ab_load32(qrow + E + c * 32, kk);
-          ab_load32(qrow + c * 32, qq);
-          ab_load32(dorow + c * 32, dd);
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            acc[e] = fmaf(ds_ii, kk[e], acc[e]);
-            qq[e] *= ds_ii;        // dK_i = dS_ii q_i
-            dd[e] *= p_ii;         // dV_i = P_ii dO_i
-          }
-          ab_store32(dq_out + E + c * 32, qq);
-          ab_store32(dq_out + 2 * E + c * 32, dd);
-        }
+        for (int e = 0; e < 32; ++e) acc[e] = __uint_as_float(raw[e]);
         if (valid) ab_store32(dq_out + c * 32, acc);
       }
-      if (nblk > 0) {
-        tc::tc_fence_before();
-        tc::mbar_arrive(dq_empty);
-      }
+      tc::tc_fence_before();
+      tc::mbar_arrive(dq_empty);
     }
   }
 
@@ -346,17 +441,17 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
   uint8_t* sK = smem;
   uint8_t* sV = smem + AB_TILE_BYTES;
   uint8_t* sQD = smem + 2 * AB_TILE_BYTES;               // stage s: Q block at +s*32K, dO block at +16K
-  float* sStat = reinterpret_cast<float*>(smem + 2 * AB_TILE_BYTES + 4 * AB_BLK_BYTES);   // [2][2][64]: lse2, delta
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * AB_TILE_BYTES + 4 * AB_BLK_BYTES + 1024);
+  float* sStat = reinterpret_cast<float*>(smem + 2 * AB_TILE_BYTES + AB_KS * 2 * AB_BLK_BYTES);   // [2][2][64]: lse2, delta*scale
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * AB_TILE_BYTES + AB_KS * 2 * AB_BLK_BYTES + 1024);
   uint64_t* kv_full = bars + 0;
   uint64_t* kv_empty = bars + 1;
-  uint64_t* qd_full = bars + 2;     // [2]
-  uint64_t* qd_empty = bars + 4;    // [2]
-  uint64_t* st_full = bars + 6;     // [2]
-  uint64_t* pds_ready = bars + 8;   // [2]
-  uint64_t* acc_done = bars + 10;
-  uint64_t* acc_empty = bars + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* qd_full = bars + 2;     // [AB_KS]
+  uint64_t* qd_empty = bars + 6;    // [AB_KS]
+  uint64_t* st_full = bars + 10;    // [2]
+  uint64_t* pds_ready = bars + 12;  // [2]
+  uint64_t* acc_done = bars + 14;
+  uint64_t* acc_empty = bars + 15;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -370,14 +465,16 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
   if (warp == 1 && lane == 0) {
     tc::mbar_init(kv_full, 1);
     tc::mbar_init(kv_empty, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < AB_KS; ++s) {
       tc::mbar_init(&qd_full[s], 1);
       tc::mbar_init(&qd_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&st_full[s], 1);
-      tc::mbar_init(&pds_ready[s], 128);
+      tc::mbar_init(&pds_ready[s], AB_EW_THREADS);
     }
     tc::mbar_init(acc_done, 1);
-    tc::mbar_init(acc_empty, 128);
+    tc::mbar_init(acc_empty, AB_EW_THREADS);
     tc::mbar_fence_init();
   }
   if (warp == 2) {
@@ -406,8 +503,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
         tc::tma_load_3d(sV, &tmQKV128, kv_full, 2 * E + h * AB_DH, b, j0);
         tc::tma_load_3d(sV + 16384, &tmQKV128, kv_full, 2 * E + h * AB_DH + 64, b, j0);
         for (int i = 0; i < nq; ++i, ++g) {
-          const int st = g & 1;
-          tc::mbar_wait(&qd_empty[st], ((g >> 1) & 1) ^ 1);
+          const int st = g % AB_KS;
+          tc::mbar_wait(&qd_empty[st], ((g / AB_KS) & 1) ^ 1);
           tc::mbar_expect_tx(&qd_full[st], 2 * AB_BLK_BYTES);
           uint8_t* qdst = sQD + st * 2 * AB_BLK_BYTES;
           uint8_t* ddst = qdst + AB_BLK_BYTES;
@@ -425,20 +522,20 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
       const uint32_t k_addr = tc::smem_u32(sK), v_addr = tc::smem_u32(sV);
       uint32_t g = 0, tcount = 0;
       auto issue_scores = [&](uint32_t gg) {
-        const uint32_t q_addr = tc::smem_u32(sQD + (gg & 1) * 2 * AB_BLK_BYTES);
+        const uint32_t q_addr = tc::smem_u32(sQD + (gg % AB_KS) * 2 * AB_BLK_BYTES);
         ab_mma_ss_128x64(tmem_base + (gg & 1) * 64, k_addr, q_addr);                        // S^T  = K Q^T
         ab_mma_ss_128x64(tmem_base + 128 + (gg & 1) * 64, v_addr, q_addr + AB_BLK_BYTES);   // dP^T = V dO^T
       };
       for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
         tc::mbar_wait(kv_full, tcount & 1);
-        tc::mbar_wait(&qd_full[g & 1], (g >> 1) & 1);
+        tc::mbar_wait(&qd_full[g % AB_KS], (g / AB_KS) & 1);
         tc::tc_fence_after();
         issue_scores(g);
         tc::umma_commit(&st_full[g & 1]);
         for (int i = 0; i < nq; ++i, ++g) {
           if (i + 1 < nq) {
             const uint32_t gn = g + 1;
-            tc::mbar_wait(&qd_full[gn & 1], (gn >> 1) & 1);
+            tc::mbar_wait(&qd_full[gn % AB_KS], (gn / AB_KS) & 1);
             tc::tc_fence_after();
             issue_scores(gn);
             tc::umma_commit(&st_full[gn & 1]);
@@ -448,10 +545,10 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
           tc::mbar_wait(&pds_ready[g & 1], (g >> 1) & 1);
           if (i == 0) tc::mbar_wait(acc_empty, (tcount & 1) ^ 1);
           tc::tc_fence_after();
-          const uint32_t q_addr = tc::smem_u32(sQD + (g & 1) * 2 * AB_BLK_BYTES);
+          const uint32_t q_addr = tc::smem_u32(sQD + (g % AB_KS) * 2 * AB_BLK_BYTES);
           ab_mma_ts_128x128(tmem_base + 256, tmem_base + (g & 1) * 64, q_addr + AB_BLK_BYTES, i > 0);   // dV += P^T dO
           ab_mma_ts_128x128(tmem_base + 384, tmem_base + 128 + (g & 1) * 64, q_addr, i > 0);            // dK += dS^T Q
-          tc::umma_commit(&qd_empty[g & 1]);
+          tc::umma_commit(&qd_empty[g % AB_KS]);
           tc::umma_commit(acc_done);
         }
       }
@@ -459,8 +556,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
     __syncwarp();
   } else {
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;              // which 32 of a block's 64 query-row columns this warp owns
     const int row = quarter * 32 + lane;           // key within the tile
-    const int st_tid = threadIdx.x - 64;           // 0..127
+    const int st_tid = threadIdx.x - 64;           // 0..255
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     uint32_t g = 0;
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
@@ -472,61 +570,66 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
       for (int i = 0; i < nq; ++i, ++g) {
         const uint32_t buf = g & 1;
         float* stat = sStat + buf * 128;
-        {
+        if (st_tid < 128) {
           const int r = i * 64 + (st_tid & 63);
           float v;
           if (st_tid < 64) v = r < p.T ? p.lse[static_cast<size_t>(bh) * p.T + r] * 1.4426950408889634f : INFINITY;
-          else v = r < p.T ? p.delta[static_cast<size_t>(bh) * p.T + r] : 0.f;
+          else v = r < p.T ? p.delta[static_cast<size_t>(bh) * p.T + r] * p.scale : 0.f;       // delta * scale
           stat[st_tid] = v;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         tc::mbar_wait(&st_full[buf], (g >> 1) & 1);
         tc::tc_fence_after();
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        {
           uint32_t s[32], dp[32], pkp[16], pkd[16];
           tc::tmem_ld_32x32b_x32(tmem_base + lane_off + buf * 64 + half * 32, s);
           tc::tmem_ld_32x32b_x32(tmem_base + lane_off + 128 + buf * 64 + half * 32, dp);
           tc::tmem_ld_wait();
+          if (key_ok) {
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            const int col = half * 32 + 2 * c;
-            const float2 l2 = *reinterpret_cast<const float2*>(&stat[col]);
-            const float2 dl = *reinterpret_cast<const float2*>(&stat[64 + col]);
-            float p0 = 0.f, p1 = 0.f;
-            if (key_ok) {
-              p0 = tc::fast_exp2(fmaf(__uint_as_float(s[2 * c]), p.scale_log2, -l2.x));
-              p1 = tc::fast_exp2(fmaf(__uint_as_float(s[2 * c + 1]), p.scale_log2, -l2.y));
+            for (int c = 0; c < 8; ++c) {
+              const int col = half * 32 + 4 * c;
+              const float4 l2 = *reinterpret_cast<const float4*>(&stat[col]);
+              const float4 dl = *reinterpret_cast<const float4*>(&stat[64 + col]);
+              const float p0 = tc::fast_exp2(fmaf(__uint_as_float(s[4 * c]), p.scale_log2, -l2.x));
+              const float p1 = tc::fast_exp2(fmaf(__uint_as_float(s[4 * c + 1]), p.scale_log2, -l2.y));
+              const float p2 = tc::fast_exp2(fmaf(__uint_as_float(s[4 * c + 2]), p.scale_log2, -l2.z));
+              const float p3 = tc::fast_exp2(fmaf(__uint_as_float(s[4 * c + 3]), p.scale_log2, -l2.w));
+              pkp[2 * c] = tc::pack_bf16x2(p0, p1);
+              pkp[2 * c + 1] = tc::pack_bf16x2(p2, p3);
+              pkd[2 * c] = tc::pack_bf16x2(p0 * fmaf(__uint_as_float(dp[4 * c]), p.scale, -dl.x),
+                                           p1 * fmaf(__uint_as_float(dp[4 * c + 1]), p.scale, -dl.y));
+              pkd[2 * c + 1] = tc::pack_bf16x2(p2 * fmaf(__uint_as_float(dp[4 * c + 2]), p.scale, -dl.z),
+                                               p3 * fmaf(__uint_as_float(dp[4 * c + 3]), p.scale, -dl.w));
             }
-            const float d0 = p0 * (__uint_as_float(dp[2 * c]) - dl.x) * p.scale;
-            const float d1 = p1 * (__uint_as_float(dp[2 * c + 1]) - dl.y) * p.scale;
-            pkp[c] = tc::pack_bf16x2(p0, p1);
-            pkd[c] = tc::pack_bf16x2(d0, d1);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) { pkp[c] = 0u; pkd[c] = 0u; }
           }
           tc::tmem_st_32x32b_x16(tmem_base + lane_off + buf * 64 + half * 16, pkp);
           tc::tmem_st_32x32b_x16(tmem_base + lane_off + 128 + buf * 64 + half * 16, pkd);
         }
         tc::tmem_st_wait();
-        if (i > 0) tc::mbar_wait(acc_done, (g - 1) & 1);   // keep in step with every acc_done phase
         tc::tc_fence_before();
         tc::mbar_arrive(&pds_ready[buf]);
       }
+      // phase-parity safety (see attention_tc.cu): observe acc_done phases g-2 then g-1, in order
+      if (nq >= 2) tc::mbar_wait(acc_done, (g - 2) & 1);
       tc::mbar_wait(acc_done, (g - 1) & 1);
       tc::tc_fence_after();
       const bool store_ok = j < p.sep && j < p.T;
-      __nv_bfloat16* drow = p.dqkv + (static_cast<size_t>(store_ok ? j : 0) * p.B + b) * p.ld_dqkv + h * AB_DH;
+      const size_t krow = p.batch_major ? static_cast<size_t>(b) * p.T + (store_ok ? j : 0) : static_cast<size_t>(store_ok ? j : 0) * p.B + b;
+      __nv_bfloat16* drow = p.dqkv + krow * p.ld_dqkv + h * AB_DH;
 #pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 4; ++c) {
         uint32_t raw[32];
         float acc[32];
-        tc::tmem_ld_32x32b_x32(tmem_base + lane_off + 256 + c * 32, raw);   // c < 4: dV, c >= 4: dK
+        // half 0 stores dV (TMEM columns 256..383), half 1 stores dK (384..511)
+        tc::tmem_ld_32x32b_x32(tmem_base + lane_off + 256 + half * 128 + c * 32, raw);
         tc::tmem_ld_wait();
 #pragma unroll
         for (int e = 0; e < 32; ++e) acc[e] = __uint_as_float(raw[e]);
-        if (store_ok) {
-          if (c < 4) ab_store32(drow + 2 * E + c * 32, acc);
-          else ab_store32(drow + E + (c - 4) * 32, acc);
-        }
+        if (store_ok) ab_store32(drow + (half == 0 ? 2 * E : E) + c * 32, acc);
       }
       tc::tc_fence_before();
       tc::mbar_arrive(acc_empty);
@@ -541,9 +644,10 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
   }
 }
 
-static int make_map3d(CUtensorMap* tm, const void* base, int ld, int width, int B, int T, int box_rows) {
+static int make_map3d(CUtensorMap* tm, const void* base, int ld, int width, int B, int T, int box_rows, int batch_major) {
   uint64_t dims[3] = {static_cast<uint64_t>(width), static_cast<uint64_t>(B), static_cast<uint64_t>(T)};
   uint64_t strides[3] = {0, static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(ld) * 2 * B};
+  if (batch_major) { strides[1] = static_cast<uint64_t>(ld) * 2 * T; strides[2] = static_cast<uint64_t>(ld) * 2; }
   uint32_t box[3] = {64, 1, static_cast<uint32_t>(box_rows)};
   return make_tensor_map_bf16(tm, base, 3, dims, strides, box, true);
 }
@@ -563,10 +667,10 @@ extern "C" int pfn_attention_bwd_tc(const pfn_attn_desc* d, void* stream) {
                 "attention_bwd_tc: buffers must be 16-byte aligned");
   const int E = d->H * d->dh;
   CUtensorMap tmQKV128, tmQKV64, tmDO128, tmDO64;
-  if (int rc = make_map3d(&tmQKV128, d->qkv, d->ld_qkv, 3 * E, d->B, d->T, 128)) return rc;
-  if (int rc = make_map3d(&tmQKV64, d->qkv, d->ld_qkv, 3 * E, d->B, d->T, 64)) return rc;
-  if (int rc = make_map3d(&tmDO128, d->dout, d->ld_dout, E, d->B, d->T, 128)) return rc;
-  if (int rc = make_map3d(&tmDO64, d->dout, d->ld_dout, E, d->B, d->T, 64)) return rc;
+  if (int rc = make_map3d(&tmQKV128, d->qkv, d->ld_qkv, 3 * E, d->B, d->T, 128, d->batch_major)) return rc;
+  if (int rc = make_map3d(&tmQKV64, d->qkv, d->ld_qkv, 3 * E, d->B, d->T, 64, d->batch_major)) return rc;
+  if (int rc = make_map3d(&tmDO128, d->dout, d->ld_dout, E, d->B, d->T, 128, d->batch_major)) return rc;
+  if (int rc = make_map3d(&tmDO64, d->dout, d->ld_dout, E, d->B, d->T, 64, d->batch_major)) return rc;
   AttnBwdParams p;
   p.T = d->T; p.B = d->B; p.H = d->H; p.sep = d->sep;
   p.scale = d->scale; p.scale_log2 = d->scale * 1.4426950408889634f;
@@ -575,6 +679,7 @@ extern "C" int pfn_attention_bwd_tc(const pfn_attn_desc* d, void* stream) {
   p.dout = reinterpret_cast<const __nv_bfloat16*>(d->dout); p.ld_dout = d->ld_dout;
   p.dqkv = reinterpret_cast<__nv_bfloat16*>(d->dqkv); p.ld_dqkv = d->ld_dqkv;
   p.lse = d->lse; p.delta = d->delta;
+  p.batch_major = d->batch_major;
   static bool attr_set = false;
   if (!attr_set) {
     PFN_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
@@ -582,6 +687,13 @@ extern "C" int pfn_attention_bwd_tc(const pfn_attn_desc* d, void* stream) {
     attr_set = true;
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  {
+    const long long rows = static_cast<long long>(d->T) * d->B;
+    long long grid = (rows + 7) / 8;
+    if (grid > 8LL * num_sms()) grid = 8LL * num_sms();
+    attn_bwd_delta_kernel<<<static_cast<int>(grid), 256, 0, s>>>(p.out, p.ld_out, p.dout, p.ld_dout, p.delta, d->T, d->B, d->H, d->batch_major);
+    PFN_LAUNCH_OK();
+  }
   {
     p.n_tiles = (d->T + 127) / 128;
     p.total_work = p.n_tiles * d->B * d->H;

@@ -173,6 +173,7 @@ static int check_attn_desc(const pfn_attn_desc* d, bool bwd, const char* who) {
   PFN_CHECK_ARG(d->sep >= 0 && d->sep <= d->T, "%s: sep %d outside [0,%d]", who, d->sep, d->T);
   PFN_CHECK_ARG(d->dtype == PFN_F32 || d->dtype == PFN_BF16, "%s: bad dtype %d", who, d->dtype);
   PFN_CHECK_ARG(d->qkv && d->out && d->lse, "%s: null qkv/out/lse", who);
+  PFN_CHECK_ARG(d->batch_major == 0 || d->batch_major == 1, "%s: bad batch_major %d", who, d->batch_major);
   PFN_CHECK_ARG(d->ld_qkv >= 3 * d->H * d->dh && d->ld_out >= d->H * d->dh, "%s: leading dims too small", who);
   if (bwd) {
     PFN_CHECK_ARG(d->dout && d->dqkv && d->delta, "%s: null dout/dqkv/delta", who);
@@ -221,12 +222,14 @@ using namespace pfn;
 
 extern "C" int pfn_attention_fwd_simt(const pfn_attn_desc* d, void* stream) {
   if (int rc = check_attn_desc(d, false, "attention_fwd_simt")) return rc;
+  PFN_CHECK_ARG(d->batch_major == 0, "attention_fwd_simt: batch-major token order is only implemented by the tcgen05 kernels");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   return d->dtype == PFN_F32 ? dispatch_attn_simt<float>(d, false, s) : dispatch_attn_simt<__nv_bfloat16>(d, false, s);
 }
 
 extern "C" int pfn_attention_bwd_simt(const pfn_attn_desc* d, void* stream) {
   if (int rc = check_attn_desc(d, true, "attention_bwd_simt")) return rc;
+  PFN_CHECK_ARG(d->batch_major == 0, "attention_bwd_simt: batch-major token order is only implemented by the tcgen05 kernels");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   return d->dtype == PFN_F32 ? dispatch_attn_simt<float>(d, true, s) : dispatch_attn_simt<__nv_bfloat16>(d, true, s);
 }

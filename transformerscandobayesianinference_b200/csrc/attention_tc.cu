@@ -42,7 +42,42 @@ struct AttnFwdParams {
   float* lse;
   int n_qtiles;
   int total_work;
+  int batch_major;
+  long long* trace;     // debug: clock64 event log of CTA 0 (null = off)
+  int trace_cap;
 };
+
+// Block plan of one 128-row query tile: `nblk` dense blocks over the train keys [0, sep), followed by up to two
+// "diagonal" blocks whose keys are the tile's own rows [i0, i0+64) / [i0+64, i0+128) — needed only when that row range
+// holds query rows (>= sep).  In a diagonal block row i keeps exactly one key: itself.  All roles call this.
+__device__ __forceinline__ int tile_block_plan(int i0, int sep, int T, int nblk, int (&dstart)[2]) {
+  int nd = 0;
+#pragma unroll
+  for (int jj = 0; jj < 2; ++jj) {
+    const int lo = i0 + 64 * jj;
+    if (lo < T && lo + 63 >= sep) dstart[nd++] = lo;
+  }
+  return nblk + nd;
+}
+
+// Debug event trace (CTA 0 only), three private regions (producer / MMA / softmax thread 64) so that logging is a plain
+// store: region r holds [ev, a, b, clock] x cap entries at trace + r*4*cap; counters live in registers of the role.
+struct AttTrace {
+  long long* base; int cap; int n;
+  __device__ __forceinline__ void log(int ev, int a, int b) {
+    if (base != nullptr && n < cap) {
+      long long* e = base + static_cast<size_t>(n) * 4;
+      e[0] = ev; e[1] = a; e[2] = b; e[3] = clock64();
+      ++n;
+    }
+  }
+};
+__device__ __forceinline__ AttTrace att_trace_make(const AttnFwdParams& p, int region) {
+  AttTrace t;
+  t.base = (p.trace != nullptr && blockIdx.x == 0) ? p.trace + static_cast<size_t>(region) * 4 * p.trace_cap : nullptr;
+  t.cap = p.trace_cap; t.n = 0;
+  return t;
+}
 
 __device__ __forceinline__ void load_row128(const __nv_bfloat16* p, float (&v)[32], int chunk) {
   // 32 consecutive bf16 -> fp32 (chunk selects which quarter of the 128-wide row)
@@ -130,7 +165,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   if (warp == 0) {
     // =============================================================== TMA producer
-    if (lane == 0 && nblk > 0) {
+    if (lane == 0) {
+      AttTrace tr = att_trace_make(p, 0);
       uint32_t g = 0;      // running KV-block counter (ring position)
       uint32_t tcount = 0; // running tile counter
       for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
@@ -138,17 +174,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int qt = w - bh * p.n_qtiles;
         const int b = bh / p.H, h = bh - b * p.H;
         const int i0 = qt * ATT_BM;
+        int dstart[2];
+        const int nb = tile_block_plan(i0, p.sep, p.T, nblk, dstart);
         tc::mbar_wait(q_empty, (tcount & 1) ^ 1);
+        tr.log(1, tcount, 0);   // Q load issue
         tc::mbar_expect_tx(q_full, ATT_Q_BYTES);
         tc::tma_load_3d(sQ, &tmQ, q_full, h * ATT_DH, b, i0);
         tc::tma_load_3d(sQ + 16384, &tmQ, q_full, h * ATT_DH + 64, b, i0);
-        for (int j = 0; j < nblk; ++j, ++g) {
+        for (int j = 0; j < nb; ++j, ++g) {
           const int st = g & 1;
           tc::mbar_wait(&kv_empty[st], ((g >> 1) & 1) ^ 1);
+          tr.log(2, tcount, j);   // KV load issue
           tc::mbar_expect_tx(&kv_full[st], 2 * ATT_KV_BYTES);
           uint8_t* kdst = sKV + st * 2 * ATT_KV_BYTES;
           uint8_t* vdst = kdst + ATT_KV_BYTES;
-          const int j0 = j * ATT_BN;
+          const int j0 = j < nblk ? j * ATT_BN : dstart[j - nblk];
           tc::tma_load_3d(kdst, &tmKV, &kv_full[st], E + h * ATT_DH, b, j0);
           tc::tma_load_3d(kdst + 8192, &tmKV, &kv_full[st], E + h * ATT_DH + 64, b, j0);
           tc::tma_load_3d(vdst, &tmKV, &kv_full[st], 2 * E + h * ATT_DH, b, j0);
@@ -159,10 +199,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __syncwarp();
   } else if (warp == 1) {
     // =============================================================== MMA issuer
-    if (lane == 0 && nblk > 0) {
+    if (lane == 0) {
       constexpr uint32_t idesc_qk = tc::umma_idesc_bf16(ATT_BM, ATT_BN, 0, 0);
       constexpr uint32_t idesc_pv = tc::umma_idesc_bf16(ATT_BM, ATT_DH, 0, 1);
       const uint32_t q_addr = tc::smem_u32(sQ);
+      AttTrace tr = att_trace_make(p, 1);
       uint32_t g = 0, tcount = 0;
       auto issue_qk = [&](uint32_t gg) {
         const int st = gg & 1;
@@ -176,15 +217,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
       };
       for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
+        const int qt = w % p.n_qtiles;
+        int dstart[2];
+        const int nb = tile_block_plan(qt * ATT_BM, p.sep, p.T, nblk, dstart);
         tc::mbar_wait(q_full, tcount & 1);
+        tr.log(10, tcount, 0);  // Q landed
         tc::mbar_wait(&kv_full[g & 1], (g >> 1) & 1);
+        tr.log(11, tcount, 0);  // KV0 landed
         tc::tc_fence_after();
         issue_qk(g);
         tc::umma_commit(&s_full[g & 1]);
-        for (int j = 0; j < nblk; ++j, ++g) {
-          if (j + 1 < nblk) {
+        for (int j = 0; j < nb; ++j, ++g) {
+          if (j + 1 < nb) {
             const uint32_t gn = g + 1;
             tc::mbar_wait(&kv_full[gn & 1], (gn >> 1) & 1);
+            tr.log(11, tcount, j + 1);
             tc::tc_fence_after();
             issue_qk(gn);
             tc::umma_commit(&s_full[gn & 1]);
@@ -192,6 +239,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             tc::umma_commit(q_empty);   // every QK^T of this tile has been issued
           }
           tc::mbar_wait(&p_ready[g & 1], (g >> 1) & 1);
+          tr.log(12, tcount, j);  // P ready seen by MMA thread
           if (j == 0) tc::mbar_wait(o_empty, (tcount & 1) ^ 1);
           tc::tc_fence_after();
           const int st = g & 1;
@@ -205,6 +253,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
           tc::umma_commit(&kv_empty[st]);
           tc::umma_commit(pv_done);
+          tr.log(13, tcount, j);  // PV issued
         }
       }
     }
@@ -214,51 +263,67 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    AttTrace tr = att_trace_make(p, 2);
     uint32_t g = 0;
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
       const int bh = w / p.n_qtiles;
       const int qt = w - bh * p.n_qtiles;
       const int b = bh / p.H, h = bh - b * p.H;
-      const int i = qt * ATT_BM + row;
+      const int i0 = qt * ATT_BM;
+      const int i = i0 + row;
       const bool valid = i < p.T;
       const bool is_query = valid && i >= p.sep;
-      const __nv_bfloat16* tok = p.qkv + (static_cast<size_t>(valid ? i : 0) * p.B + b) * p.ld_qkv + h * ATT_DH;
-      float m = -INFINITY, l = 0.f, t_ii = 0.f;
-      if (is_query) {
-        t_ii = dot_rows128(tok, tok + E) * p.scale_log2;
-        m = t_ii;
-        l = 1.0f;
-      }
-      for (int j = 0; j < nblk; ++j, ++g) {
+      int dstart[2];
+      const int nb = tile_block_plan(i0, p.sep, p.T, nblk, dstart);
+      float m = -INFINITY, l = 0.f;
+      for (int j = 0; j < nb; ++j, ++g) {
         const uint32_t buf = g & 1;
         tc::mbar_wait(&s_full[buf], (g >> 1) & 1);
+        if (threadIdx.x == 64) tr.log(20, w, j);   // S visible to softmax
         tc::tc_fence_after();
         const uint32_t s_tmem = tmem_base + lane_off + buf * ATT_BN;
         uint32_t r0[32], r1[32];
         tc::tmem_ld_32x32b_x32(s_tmem, r0);
         tc::tmem_ld_32x32b_x32(s_tmem + 32, r1);
         tc::tmem_ld_wait();
-        const int kmax = p.sep - j * ATT_BN;   // number of valid keys in this block (>= 1)
+        // keys of this block the row may attend to: all 64 (full dense block), the first kmax (last dense block), or
+        // only the row's own key (diagonal block).  Three code paths so that the common one carries no masks.
+        const bool dense = j < nblk;
+        const int kmax = dense ? p.sep - j * ATT_BN : 0;
+        int c_self = -1;
+        if (!dense) {
+          const int c = i - dstart[j - nblk];
+          if (is_query && c >= 0 && c < ATT_BN) c_self = c;
+        }
         float bm = -INFINITY;
+        if (dense && kmax >= ATT_BN) {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          if (c < kmax) bm = fmaxf(bm, __uint_as_float(r0[c]));
-          if (c + 32 < kmax) bm = fmaxf(bm, __uint_as_float(r1[c]));
+          for (int c = 0; c < 32; ++c) bm = fmaxf(bm, fmaxf(__uint_as_float(r0[c]), __uint_as_float(r1[c])));
+        } else if (dense) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            if (c < kmax) bm = fmaxf(bm, __uint_as_float(r0[c]));
+            if (c + 32 < kmax) bm = fmaxf(bm, __uint_as_float(r1[c]));
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            bm = (c == c_self) ? __uint_as_float(r0[c]) : bm;
+            bm = (c + 32 == c_self) ? __uint_as_float(r1[c]) : bm;
+          }
         }
         bm *= p.scale_log2;
-        const bool need = bm > m + kRescaleThreshold;   // also true when m == -inf
-        // Observe EVERY pv_done phase in order (a parity wait that runs two phases ahead of the barrier would pass
-        // spuriously): block g-1's P V must be complete before O may be rescaled and before P_g is published.
-        if (j > 0) {
-          tc::mbar_wait(pv_done, (g - 1) & 1);
-          tc::tc_fence_after();
-        }
+        const bool need = bm > m + kRescaleThreshold;   // also true when m == -inf and the block has a visible key
         if (__any_sync(0xffffffffu, need)) {
           const float m_new = need ? bm : m;
           const float factor = need ? tc::fast_exp2(m - m_new) : 1.0f;   // exp2(-inf) = 0
           l *= factor;
           m = m_new;
           if (j > 0) {
+            // P V of block g-1 must be complete before O is rescaled.  Safe w.r.t. phase parity: this thread has seen
+            // S_g, which was issued after P V of block g-2, so pv_done is at phase g-1 or g.
+            tc::mbar_wait(pv_done, (g - 1) & 1);
+            tc::tc_fence_after();
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
               uint32_t o[32];
@@ -274,66 +339,77 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         uint32_t pk[32];
         float psum = 0.f;
+        if (dense && kmax >= ATT_BN) {
+          const float nm = -m;
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          const float a0 = (2 * c < kmax) ? tc::fast_exp2(fmaf(__uint_as_float(r0[2 * c]), p.scale_log2, -m)) : 0.f;
-          const float a1 = (2 * c + 1 < kmax) ? tc::fast_exp2(fmaf(__uint_as_float(r0[2 * c + 1]), p.scale_log2, -m)) : 0.f;
-          const float b0 = (2 * c + 32 < kmax) ? tc::fast_exp2(fmaf(__uint_as_float(r1[2 * c]), p.scale_log2, -m)) : 0.f;
-          const float b1 = (2 * c + 33 < kmax) ? tc::fast_exp2(fmaf(__uint_as_float(r1[2 * c + 1]), p.scale_log2, -m)) : 0.f;
-          psum += (a0 + a1) + (b0 + b1);
-          pk[c] = tc::pack_bf16x2(a0, a1);
-          pk[16 + c] = tc::pack_bf16x2(b0, b1);
+          for (int c = 0; c < 16; ++c) {
+            const float a0 = tc::fast_exp2(fmaf(__uint_as_float(r0[2 * c]), p.scale_log2, nm));
+            const float a1 = tc::fast_exp2(fmaf(__uint_as_float(r0[2 * c + 1]), p.scale_log2, nm));
+            const float b0 = tc::fast_exp2(fmaf(__uint_as_float(r1[2 * c]), p.scale_log2, nm));
+            const float b1 = tc::fast_exp2(fmaf(__uint_as_float(r1[2 * c + 1]), p.scale_log2, nm));
+            psum += (a0 + a1) + (b0 + b1);
+            pk[c] = tc::pack_bf16x2(a0, a1);
+            pk[16 + c] = tc::pack_bf16x2(b0, b1);
+          }
+        } else if (dense) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const float a0 = (2 * c < kmax) ? tc::fast_exp2(fmaf(__uint_as_float(r0[2 * c]), p.scale_log2, -m)) : 0.f;
+            const float a1 = (2 * c + 1 < kmax) ? tc::fast_exp2(fmaf(__uint_as_float(r0[2 * c + 1]), p.scale_log2, -m)) : 0.f;
+            const float b0 = (2 * c + 32 < kmax) ? tc::fast_exp2(fmaf(__uint_as_float(r1[2 * c]), p.scale_log2, -m)) : 0.f;
+            const float b1 = (2 * c + 33 < kmax) ? tc::fast_exp2(fmaf(__uint_as_float(r1[2 * c + 1]), p.scale_log2, -m)) : 0.f;
+            psum += (a0 + a1) + (b0 + b1);
+            pk[c] = tc::pack_bf16x2(a0, a1);
+            pk[16 + c] = tc::pack_bf16x2(b0, b1);
+          }
+        } else {
+          // bm is the row's own (scaled) score when it has one; everything else in the block is masked
+          const float pself = c_self >= 0 ? tc::fast_exp2(bm - m) : 0.f;
+          psum = pself;
+          const uint32_t lo = tc::pack_bf16x2(pself, 0.f), hi = tc::pack_bf16x2(0.f, pself);
+          const int cw = c_self >> 1;                      // packed column holding the key (-1 >> 1 == -1: none)
+          const uint32_t word = (c_self & 1) ? hi : lo;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) pk[c] = (c == cw) ? word : 0u;
         }
         l += psum;
         tc::tmem_st_32x32b_x32(tmem_base + lane_off + buf * ATT_BN, pk);
         tc::tmem_st_wait();
         tc::tc_fence_before();
         tc::mbar_arrive(&p_ready[buf]);
+        if (threadIdx.x == 64) tr.log(21, w, j);   // P published
       }
-      // ---- epilogue: O / l (+ diagonal key), lse
-      if (nblk > 0) {
-        tc::mbar_wait(pv_done, (g - 1) & 1);
-        tc::tc_fence_after();
-      }
-      const float pd = is_query ? tc::fast_exp2(t_ii - m) : 0.f;
+      // ---- epilogue: O / l, lse   (every valid row has seen at least one key: a train key or itself)
+      // Phase-parity safety: having seen the last S, this thread knows P V of block nb-3 is complete, so pv_done is at
+      // most two phases behind; observe phase g-2 (if any in this tile) and then g-1, in order.
+      if (nb >= 2) tc::mbar_wait(pv_done, (g - 2) & 1);
+      tc::mbar_wait(pv_done, (g - 1) & 1);
+      if (threadIdx.x == 64) tr.log(22, w, 0);     // epilogue start
+      tc::tc_fence_after();
       const float inv_l = 1.0f / l;
-      __nv_bfloat16* orow = p.out + (static_cast<size_t>(valid ? i : 0) * p.B + b) * p.ld_out + h * ATT_DH;
+      const size_t tokrow = p.batch_major ? static_cast<size_t>(b) * p.T + (valid ? i : 0) : static_cast<size_t>(valid ? i : 0) * p.B + b;
+      __nv_bfloat16* orow = p.out + tokrow * p.ld_out + h * ATT_DH;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
-        float o[32];
-        if (nblk > 0) {
-          uint32_t raw[32];
-          tc::tmem_ld_32x32b_x32(tmem_base + lane_off + 128 + c * 32, raw);
-          tc::tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 32; ++e) o[e] = __uint_as_float(raw[e]);
-        } else {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) o[e] = 0.f;
-        }
-        if (is_query) {
-          float vv[32];
-          load_row128(tok + 2 * E, vv, c);
-#pragma unroll
-          for (int e = 0; e < 32; ++e) o[e] = fmaf(pd, vv[e], o[e]);
-        }
+        uint32_t raw[32];
+        tc::tmem_ld_32x32b_x32(tmem_base + lane_off + 128 + c * 32, raw);
+        tc::tmem_ld_wait();
         if (valid) {
 #pragma unroll
           for (int e = 0; e < 32; e += 8) {
             uint4 pk4;
-            pk4.x = tc::pack_bf16x2(o[e] * inv_l, o[e + 1] * inv_l);
-            pk4.y = tc::pack_bf16x2(o[e + 2] * inv_l, o[e + 3] * inv_l);
-            pk4.z = tc::pack_bf16x2(o[e + 4] * inv_l, o[e + 5] * inv_l);
-            pk4.w = tc::pack_bf16x2(o[e + 6] * inv_l, o[e + 7] * inv_l);
+            pk4.x = tc::pack_bf16x2(__uint_as_float(raw[e]) * inv_l, __uint_as_float(raw[e + 1]) * inv_l);
+            pk4.y = tc::pack_bf16x2(__uint_as_float(raw[e + 2]) * inv_l, __uint_as_float(raw[e + 3]) * inv_l);
+            pk4.z = tc::pack_bf16x2(__uint_as_float(raw[e + 4]) * inv_l, __uint_as_float(raw[e + 5]) * inv_l);
+            pk4.w = tc::pack_bf16x2(__uint_as_float(raw[e + 6]) * inv_l, __uint_as_float(raw[e + 7]) * inv_l);
             *reinterpret_cast<uint4*>(orow + c * 32 + e) = pk4;
           }
         }
       }
       if (valid) p.lse[static_cast<size_t>(bh) * p.T + i] = (m + log2f(l)) * 0.6931471805599453f;
-      if (nblk > 0) {
-        tc::tc_fence_before();
-        tc::mbar_arrive(o_empty);
-      }
+      tc::tc_fence_before();
+      tc::mbar_arrive(o_empty);
+      if (threadIdx.x == 64) tr.log(23, w, 0);     // epilogue end
     }
   }
 
@@ -345,9 +421,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 }
 
-static int make_qkv_map(CUtensorMap* tm, const void* base, int ld, int width, int B, int T, int box_rows) {
+static long long* g_trace_ptr = nullptr;
+static int g_trace_cap = 0;
+
+static int make_qkv_map(CUtensorMap* tm, const void* base, int ld, int width, int B, int T, int box_rows, int batch_major) {
   uint64_t dims[3] = {static_cast<uint64_t>(width), static_cast<uint64_t>(B), static_cast<uint64_t>(T)};
   uint64_t strides[3] = {0, static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(ld) * 2 * B};
+  if (batch_major) { strides[1] = static_cast<uint64_t>(ld) * 2 * T; strides[2] = static_cast<uint64_t>(ld) * 2; }
   uint32_t box[3] = {64, 1, static_cast<uint32_t>(box_rows)};
   return make_tensor_map_bf16(tm, base, 3, dims, strides, box, true);
 }
@@ -370,8 +450,8 @@ extern "C" int pfn_attention_fwd_tc(const pfn_attn_desc* d, void* stream) {
   if (int rc = check_tc_attn(d, "attention_fwd_tc")) return rc;
   CUtensorMap tmQ, tmKV;
   const int E = d->H * d->dh;
-  if (int rc = make_qkv_map(&tmQ, d->qkv, d->ld_qkv, 3 * E, d->B, d->T, ATT_BM)) return rc;
-  if (int rc = make_qkv_map(&tmKV, d->qkv, d->ld_qkv, 3 * E, d->B, d->T, ATT_BN)) return rc;
+  if (int rc = make_qkv_map(&tmQ, d->qkv, d->ld_qkv, 3 * E, d->B, d->T, ATT_BM, d->batch_major)) return rc;
+  if (int rc = make_qkv_map(&tmKV, d->qkv, d->ld_qkv, 3 * E, d->B, d->T, ATT_BN, d->batch_major)) return rc;
   AttnFwdParams p;
   p.T = d->T; p.B = d->B; p.H = d->H; p.sep = d->sep;
   p.scale_log2 = d->scale * 1.4426950408889634f;
@@ -380,6 +460,9 @@ extern "C" int pfn_attention_fwd_tc(const pfn_attn_desc* d, void* stream) {
   p.lse = d->lse;
   p.n_qtiles = (d->T + ATT_BM - 1) / ATT_BM;
   p.total_work = p.n_qtiles * d->B * d->H;
+  p.batch_major = d->batch_major;
+  p.trace = g_trace_ptr;
+  p.trace_cap = g_trace_cap;
   static bool attr_set = false;
   if (!attr_set) {
     PFN_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWD_SMEM));
@@ -390,5 +473,13 @@ extern "C" int pfn_attention_fwd_tc(const pfn_attn_desc* d, void* stream) {
   if (grid > p.total_work) grid = p.total_work;
   attn_fwd_tc_kernel<<<grid, ATT_THREADS, ATT_FWD_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmKV, p);
   PFN_LAUNCH_OK();
+  return 0;
+}
+
+// Debug hook (not part of the product API surface): log clock64 events of CTA 0 of subsequent forward launches into
+// `buf` ([1 + 4*cap] int64, first element = event count; zero it before the launch).  Pass null to switch off.
+extern "C" int pfn_debug_attention_trace(long long* buf, int cap) {
+  g_trace_ptr = buf;
+  g_trace_cap = cap;
   return 0;
 }
