@@ -87,8 +87,8 @@ int pfn_attention_fwd_simt(const pfn_attn_desc* d, void* stream);
 int pfn_attention_bwd_simt(const pfn_attn_desc* d, void* stream);
 int pfn_attention_fwd_tc(const pfn_attn_desc* d, void* stream);
 int pfn_attention_bwd_tc(const pfn_attn_desc* d, void* stream);
-/* debug: clock64 event log of CTA 0 of subsequent pfn_attention_fwd_tc launches ([1 + 4*cap] int64; null = off) */
-int pfn_debug_attention_trace(long long* buf, int cap);
+/* debug: clock64 event log of CTA 0 of subsequent tcgen05 attention launches ([3][cap][4] int64; which: 0 fwd, 1 dq, 2 dkv; null = off) */
+int pfn_debug_attention_trace(long long* buf, int cap, int which);
 
 /* ------------------------------------------------------------------------------------------------
  * Embedding stage (reference transformer.py:68-74):

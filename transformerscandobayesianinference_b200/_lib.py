@@ -94,7 +94,7 @@ def load():
     lib.pfn_gemm_simt.argtypes = [ctypes.POINTER(GemmDesc), c_void_p]
     for n in ("pfn_attention_fwd_simt", "pfn_attention_bwd_simt", "pfn_attention_fwd_tc", "pfn_attention_bwd_tc"):
         getattr(lib, n).argtypes = [ctypes.POINTER(AttnDesc), c_void_p]
-    lib.pfn_debug_attention_trace.argtypes = [c_void_p, c_int]
+    lib.pfn_debug_attention_trace.argtypes = [c_void_p, c_int, c_int]
     lib.pfn_embed_fwd.argtypes = [c_void_p] * 7 + [c_int] * 6 + [c_void_p]
     lib.pfn_embed_bwd.argtypes = [c_void_p, c_int] + [c_void_p] * 6 + [c_int] * 5 + [c_void_p]
     lib.pfn_layernorm_fwd.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,

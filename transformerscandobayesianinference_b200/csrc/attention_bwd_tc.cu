@@ -30,6 +30,7 @@ int check_attn_desc_public(const pfn_attn_desc* d, bool bwd, const char* who);
 constexpr int AB_DH = 128;
 constexpr int AB_THREADS = 320;                   // warp 0 TMA, warp 1 MMA, warps 2..9 elementwise (2 per TMEM lane quarter)
 constexpr int AB_EW_THREADS = 256;
+constexpr int AB_EW_WARPS = 8;
 constexpr int AB_TILE_BYTES = 128 * AB_DH * 2;     // 32 KB : 128-row operand tile (2 chunks of 16 KB)
 constexpr int AB_BLK_BYTES = 64 * AB_DH * 2;       // 16 KB : 64-row operand block (2 chunks of 8 KB)
 constexpr int AB_KS = 4;                           // depth of the 64-row block ring (TMA runs 3 blocks ahead of the MMAs)
@@ -47,6 +48,7 @@ struct AttnBwdParams {
   int n_tiles;
   int total_work;
   int batch_major;
+  long long* trace; int trace_cap;
 };
 
 __device__ __forceinline__ void ab_load32(const __nv_bfloat16* p, float (&v)[32]) {
@@ -94,6 +96,7 @@ __device__ __forceinline__ float ab_dot128(const __nv_bfloat16* a, const __nv_bf
 }
 
 // 128x64x128 SS MMA: D[tmem] = A[128 rows x 128 dh, K-major tile] * B[64 rows x 128 dh, K-major block]^T
+// (all ab_mma_* helpers must be called by exactly one elected lane of a converged warp)
 __device__ __forceinline__ void ab_mma_ss_128x64(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr) {
   constexpr uint32_t idesc = tc::umma_idesc_bf16(128, 64, 0, 0);
 #pragma unroll
@@ -212,17 +215,17 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
   }
   if (warp == 1 && lane == 0) {
     tc::mbar_init(qdo_full, 1);
-    tc::mbar_init(qdo_empty, 1 + AB_EW_THREADS);   // MMA commit (score MMAs done) + every row thread (smem row reads done)
+    tc::mbar_init(qdo_empty, 1 + AB_EW_WARPS);   // MMA commit (score MMAs done) + every row thread (smem row reads done)
     for (int s = 0; s < AB_KS; ++s) {
       tc::mbar_init(&kv_full[s], 1);
       tc::mbar_init(&kv_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&s_full[s], 1);
-      tc::mbar_init(&ds_ready[s], AB_EW_THREADS);
+      tc::mbar_init(&ds_ready[s], AB_EW_WARPS);
     }
     tc::mbar_init(dq_done, 1);
-    tc::mbar_init(dq_empty, AB_EW_THREADS);
+    tc::mbar_init(dq_empty, AB_EW_WARPS);
     tc::mbar_fence_init();
   }
   if (warp == 2) {
@@ -237,7 +240,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
   // TMEM columns: S[2] @0,64 | dP[2] @128,192 | dQ @256..383
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
+      tc::KernelTrace tr = tc::trace_make(p.trace, p.trace_cap, 0);
       uint32_t g = 0, tcount = 0;
       for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
         const int bh = w / p.n_tiles;
@@ -247,70 +251,89 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
         int dstart[2];
         const int nb = ab_tile_block_plan(i0, p.sep, p.T, nblk, dstart);
         tc::mbar_wait(qdo_empty, (tcount & 1) ^ 1);
-        tc::mbar_expect_tx(qdo_full, 2 * AB_TILE_BYTES);
-        tc::tma_load_3d(sQ, &tmQKV128, qdo_full, h * AB_DH, b, i0);
-        tc::tma_load_3d(sQ + 16384, &tmQKV128, qdo_full, h * AB_DH + 64, b, i0);
-        tc::tma_load_3d(sDO, &tmDO128, qdo_full, h * AB_DH, b, i0);
-        tc::tma_load_3d(sDO + 16384, &tmDO128, qdo_full, h * AB_DH + 64, b, i0);
+        if (lane == 0) tr.log(1, tcount, 0);
+        if (tc::elect_one()) {
+          tc::mbar_expect_tx(qdo_full, 2 * AB_TILE_BYTES);
+          tc::tma_load_3d(sQ, &tmQKV128, qdo_full, h * AB_DH, b, i0);
+          tc::tma_load_3d(sQ + 16384, &tmQKV128, qdo_full, h * AB_DH + 64, b, i0);
+          tc::tma_load_3d(sDO, &tmDO128, qdo_full, h * AB_DH, b, i0);
+          tc::tma_load_3d(sDO + 16384, &tmDO128, qdo_full, h * AB_DH + 64, b, i0);
+        }
+        __syncwarp();
         for (int j = 0; j < nb; ++j, ++g) {
           const int st = g % AB_KS;
           tc::mbar_wait(&kv_empty[st], ((g / AB_KS) & 1) ^ 1);
-          tc::mbar_expect_tx(&kv_full[st], 2 * AB_BLK_BYTES);
+          if (lane == 0) tr.log(2, tcount, j);
           uint8_t* kdst = sKV + st * 2 * AB_BLK_BYTES;
           uint8_t* vdst = kdst + AB_BLK_BYTES;
           const int j0 = j < nblk ? j * 64 : dstart[j - nblk];
-          tc::tma_load_3d(kdst, &tmQKV64, &kv_full[st], E + h * AB_DH, b, j0);
-          tc::tma_load_3d(kdst + 8192, &tmQKV64, &kv_full[st], E + h * AB_DH + 64, b, j0);
-          tc::tma_load_3d(vdst, &tmQKV64, &kv_full[st], 2 * E + h * AB_DH, b, j0);
-          tc::tma_load_3d(vdst + 8192, &tmQKV64, &kv_full[st], 2 * E + h * AB_DH + 64, b, j0);
+          if (tc::elect_one()) {
+            tc::mbar_expect_tx(&kv_full[st], 2 * AB_BLK_BYTES);
+            tc::tma_load_3d(kdst, &tmQKV64, &kv_full[st], E + h * AB_DH, b, j0);
+            tc::tma_load_3d(kdst + 8192, &tmQKV64, &kv_full[st], E + h * AB_DH + 64, b, j0);
+            tc::tma_load_3d(vdst, &tmQKV64, &kv_full[st], 2 * E + h * AB_DH, b, j0);
+            tc::tma_load_3d(vdst + 8192, &tmQKV64, &kv_full[st], 2 * E + h * AB_DH + 64, b, j0);
+          }
+          __syncwarp();
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      tc::KernelTrace tr = tc::trace_make(p.trace, p.trace_cap, 1);
       uint32_t g = 0, tcount = 0;
+      const uint32_t q_addr = tc::smem_u32(sQ), do_addr = tc::smem_u32(sDO);
+      auto issue_scores = [&](uint32_t gg) {
+        const uint32_t k_addr = tc::smem_u32(sKV + (gg % AB_KS) * 2 * AB_BLK_BYTES);
+        if (tc::elect_one()) {
+          ab_mma_ss_128x64(tmem_base + (gg & 1) * 64, q_addr, k_addr);                       // S  = Q K^T
+          ab_mma_ss_128x64(tmem_base + 128 + (gg & 1) * 64, do_addr, k_addr + AB_BLK_BYTES); // dP = dO V^T
+          tc::umma_commit(&s_full[gg & 1]);
+        }
+        __syncwarp();
+      };
       for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
         const int qt = w % p.n_tiles;
         int dstart[2];
         const int nb = ab_tile_block_plan(qt * 128, p.sep, p.T, nblk, dstart);
-        const uint32_t q_addr = tc::smem_u32(sQ), do_addr = tc::smem_u32(sDO);
-        auto issue_scores = [&](uint32_t gg) {
-          const uint32_t k_addr = tc::smem_u32(sKV + (gg % AB_KS) * 2 * AB_BLK_BYTES);
-          ab_mma_ss_128x64(tmem_base + (gg & 1) * 64, q_addr, k_addr);                       // S  = Q K^T
-          ab_mma_ss_128x64(tmem_base + 128 + (gg & 1) * 64, do_addr, k_addr + AB_BLK_BYTES); // dP = dO V^T
-        };
         tc::mbar_wait(qdo_full, tcount & 1);
+        if (lane == 0) tr.log(10, tcount, 0);
         tc::mbar_wait(&kv_full[g % AB_KS], (g / AB_KS) & 1);
+        if (lane == 0) tr.log(11, tcount, 0);
         tc::tc_fence_after();
         issue_scores(g);
-        tc::umma_commit(&s_full[g & 1]);
         for (int j = 0; j < nb; ++j, ++g) {
           if (j + 1 < nb) {
             const uint32_t gn = g + 1;
             tc::mbar_wait(&kv_full[gn % AB_KS], (gn / AB_KS) & 1);
+            if (lane == 0) tr.log(11, tcount, j + 1);
             tc::tc_fence_after();
             issue_scores(gn);
-            tc::umma_commit(&s_full[gn & 1]);
           } else {
-            tc::umma_commit(qdo_empty);
+            if (tc::elect_one()) tc::umma_commit(qdo_empty);
+            __syncwarp();
           }
           tc::mbar_wait(&ds_ready[g & 1], (g >> 1) & 1);
+          if (lane == 0) tr.log(12, tcount, j);
           if (j == 0) tc::mbar_wait(dq_empty, (tcount & 1) ^ 1);
           tc::tc_fence_after();
           const uint32_t k_addr = tc::smem_u32(sKV + (g % AB_KS) * 2 * AB_BLK_BYTES);
-          ab_mma_ts_128x128(tmem_base + 256, tmem_base + (g & 1) * 64, k_addr, j > 0);     // dQ += dS K
-          tc::umma_commit(&kv_empty[g % AB_KS]);
-          tc::umma_commit(dq_done);
+          if (tc::elect_one()) {
+            ab_mma_ts_128x128(tmem_base + 256, tmem_base + (g & 1) * 64, k_addr, j > 0);     // dQ += dS K
+            tc::umma_commit(&kv_empty[g % AB_KS]);
+            tc::umma_commit(dq_done);
+          }
+          __syncwarp();
+          if (lane == 0) tr.log(13, tcount, j);
         }
       }
     }
-    __syncwarp();
   } else {
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may touch
     const int half = (warp - 2) >> 2;             // which 32 of a block's 64 key columns this warp owns
     const int row = quarter * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    tc::KernelTrace tr = tc::trace_make(p.trace, p.trace_cap, warp);   // one region per elementwise warp (2..9)
     uint32_t g = 0, tcount = 0;
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
       const int bh = w / p.n_tiles;
@@ -331,6 +354,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
       for (int j = 0; j < nb; ++j, ++g) {
         const uint32_t buf = g & 1;
         tc::mbar_wait(&s_full[buf], (g >> 1) & 1);
+        if (lane == 0) tr.log(20 + 100 * warp, tcount, j);
         tc::tc_fence_after();
         const bool dense = j < nblk;
         const int kmax = dense ? p.sep - j * 64 : 0;
@@ -397,12 +421,14 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
         tc::tmem_st_32x32b_x16(tmem_base + lane_off + buf * 64 + half * 16, pk);
         tc::tmem_st_wait();
         tc::tc_fence_before();
-        tc::mbar_arrive(&ds_ready[buf]);
+        tc::mbar_arrive_warp(&ds_ready[buf]);
+        if (lane == 0) tr.log(21 + 100 * warp, tcount, j);
       }
-      tc::mbar_arrive(qdo_empty);                        // this thread no longer reads the Q / dO tiles
+      tc::mbar_arrive_warp(qdo_empty);                        // this thread no longer reads the Q / dO tiles
       // phase-parity safety (see attention_tc.cu): observe dq_done phases g-2 then g-1, in order
       if (nb >= 2) tc::mbar_wait(dq_done, (g - 2) & 1);
       tc::mbar_wait(dq_done, (g - 1) & 1);
+      if (lane == 0) tr.log(22 + 100 * warp, tcount, 0);
       tc::tc_fence_after();
       const size_t tok = p.batch_major ? static_cast<size_t>(b) * p.T + (valid ? i : 0) : static_cast<size_t>(valid ? i : 0) * p.B + b;
       __nv_bfloat16* dq_out = p.dqkv + tok * p.ld_dqkv + h * AB_DH;
@@ -418,7 +444,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
         if (valid) ab_store32(dq_out + c * 32, acc);
       }
       tc::tc_fence_before();
-      tc::mbar_arrive(dq_empty);
+      tc::mbar_arrive_warp(dq_empty);
+      if (lane == 0) tr.log(23 + 100 * warp, tcount, 0);
     }
   }
 
@@ -471,10 +498,10 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
     }
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&st_full[s], 1);
-      tc::mbar_init(&pds_ready[s], AB_EW_THREADS);
+      tc::mbar_init(&pds_ready[s], AB_EW_WARPS);
     }
     tc::mbar_init(acc_done, 1);
-    tc::mbar_init(acc_empty, AB_EW_THREADS);
+    tc::mbar_init(acc_empty, AB_EW_WARPS);
     tc::mbar_fence_init();
   }
   if (warp == 2) {
@@ -489,7 +516,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
   // TMEM columns: S^T[2] @0,64 | dP^T[2] @128,192 | dV @256 | dK @384
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       uint32_t g = 0, tcount = 0;
       for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
         const int bh = w / p.n_tiles;
@@ -497,63 +524,73 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
         const int b = bh / p.H, h = bh - b * p.H;
         const int j0 = kt * 128;
         tc::mbar_wait(kv_empty, (tcount & 1) ^ 1);
-        tc::mbar_expect_tx(kv_full, 2 * AB_TILE_BYTES);
-        tc::tma_load_3d(sK, &tmQKV128, kv_full, E + h * AB_DH, b, j0);
-        tc::tma_load_3d(sK + 16384, &tmQKV128, kv_full, E + h * AB_DH + 64, b, j0);
-        tc::tma_load_3d(sV, &tmQKV128, kv_full, 2 * E + h * AB_DH, b, j0);
-        tc::tma_load_3d(sV + 16384, &tmQKV128, kv_full, 2 * E + h * AB_DH + 64, b, j0);
+        if (tc::elect_one()) {
+          tc::mbar_expect_tx(kv_full, 2 * AB_TILE_BYTES);
+          tc::tma_load_3d(sK, &tmQKV128, kv_full, E + h * AB_DH, b, j0);
+          tc::tma_load_3d(sK + 16384, &tmQKV128, kv_full, E + h * AB_DH + 64, b, j0);
+          tc::tma_load_3d(sV, &tmQKV128, kv_full, 2 * E + h * AB_DH, b, j0);
+          tc::tma_load_3d(sV + 16384, &tmQKV128, kv_full, 2 * E + h * AB_DH + 64, b, j0);
+        }
+        __syncwarp();
         for (int i = 0; i < nq; ++i, ++g) {
           const int st = g % AB_KS;
           tc::mbar_wait(&qd_empty[st], ((g / AB_KS) & 1) ^ 1);
-          tc::mbar_expect_tx(&qd_full[st], 2 * AB_BLK_BYTES);
           uint8_t* qdst = sQD + st * 2 * AB_BLK_BYTES;
           uint8_t* ddst = qdst + AB_BLK_BYTES;
           const int i0 = i * 64;
-          tc::tma_load_3d(qdst, &tmQKV64, &qd_full[st], h * AB_DH, b, i0);
-          tc::tma_load_3d(qdst + 8192, &tmQKV64, &qd_full[st], h * AB_DH + 64, b, i0);
-          tc::tma_load_3d(ddst, &tmDO64, &qd_full[st], h * AB_DH, b, i0);
-          tc::tma_load_3d(ddst + 8192, &tmDO64, &qd_full[st], h * AB_DH + 64, b, i0);
+          if (tc::elect_one()) {
+            tc::mbar_expect_tx(&qd_full[st], 2 * AB_BLK_BYTES);
+            tc::tma_load_3d(qdst, &tmQKV64, &qd_full[st], h * AB_DH, b, i0);
+            tc::tma_load_3d(qdst + 8192, &tmQKV64, &qd_full[st], h * AB_DH + 64, b, i0);
+            tc::tma_load_3d(ddst, &tmDO64, &qd_full[st], h * AB_DH, b, i0);
+            tc::tma_load_3d(ddst + 8192, &tmDO64, &qd_full[st], h * AB_DH + 64, b, i0);
+          }
+          __syncwarp();
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t k_addr = tc::smem_u32(sK), v_addr = tc::smem_u32(sV);
       uint32_t g = 0, tcount = 0;
       auto issue_scores = [&](uint32_t gg) {
         const uint32_t q_addr = tc::smem_u32(sQD + (gg % AB_KS) * 2 * AB_BLK_BYTES);
-        ab_mma_ss_128x64(tmem_base + (gg & 1) * 64, k_addr, q_addr);                        // S^T  = K Q^T
-        ab_mma_ss_128x64(tmem_base + 128 + (gg & 1) * 64, v_addr, q_addr + AB_BLK_BYTES);   // dP^T = V dO^T
+        if (tc::elect_one()) {
+          ab_mma_ss_128x64(tmem_base + (gg & 1) * 64, k_addr, q_addr);                        // S^T  = K Q^T
+          ab_mma_ss_128x64(tmem_base + 128 + (gg & 1) * 64, v_addr, q_addr + AB_BLK_BYTES);   // dP^T = V dO^T
+          tc::umma_commit(&st_full[gg & 1]);
+        }
+        __syncwarp();
       };
       for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
         tc::mbar_wait(kv_full, tcount & 1);
         tc::mbar_wait(&qd_full[g % AB_KS], (g / AB_KS) & 1);
         tc::tc_fence_after();
         issue_scores(g);
-        tc::umma_commit(&st_full[g & 1]);
         for (int i = 0; i < nq; ++i, ++g) {
           if (i + 1 < nq) {
             const uint32_t gn = g + 1;
             tc::mbar_wait(&qd_full[gn % AB_KS], (gn / AB_KS) & 1);
             tc::tc_fence_after();
             issue_scores(gn);
-            tc::umma_commit(&st_full[gn & 1]);
           } else {
-            tc::umma_commit(kv_empty);
+            if (tc::elect_one()) tc::umma_commit(kv_empty);
+            __syncwarp();
           }
           tc::mbar_wait(&pds_ready[g & 1], (g >> 1) & 1);
           if (i == 0) tc::mbar_wait(acc_empty, (tcount & 1) ^ 1);
           tc::tc_fence_after();
           const uint32_t q_addr = tc::smem_u32(sQD + (g % AB_KS) * 2 * AB_BLK_BYTES);
-          ab_mma_ts_128x128(tmem_base + 256, tmem_base + (g & 1) * 64, q_addr + AB_BLK_BYTES, i > 0);   // dV += P^T dO
-          ab_mma_ts_128x128(tmem_base + 384, tmem_base + 128 + (g & 1) * 64, q_addr, i > 0);            // dK += dS^T Q
-          tc::umma_commit(&qd_empty[g % AB_KS]);
-          tc::umma_commit(acc_done);
+          if (tc::elect_one()) {
+            ab_mma_ts_128x128(tmem_base + 256, tmem_base + (g & 1) * 64, q_addr + AB_BLK_BYTES, i > 0);   // dV += P^T dO
+            ab_mma_ts_128x128(tmem_base + 384, tmem_base + 128 + (g & 1) * 64, q_addr, i > 0);            // dK += dS^T Q
+            tc::umma_commit(&qd_empty[g % AB_KS]);
+            tc::umma_commit(acc_done);
+          }
+          __syncwarp();
         }
       }
     }
-    __syncwarp();
   } else {
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;              // which 32 of a block's 64 query-row columns this warp owns
@@ -611,7 +648,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
         }
         tc::tmem_st_wait();
         tc::tc_fence_before();
-        tc::mbar_arrive(&pds_ready[buf]);
+        tc::mbar_arrive_warp(&pds_ready[buf]);
       }
       // phase-parity safety (see attention_tc.cu): observe acc_done phases g-2 then g-1, in order
       if (nq >= 2) tc::mbar_wait(acc_done, (g - 2) & 1);
@@ -632,7 +669,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
         if (store_ok) ab_store32(drow + (half == 0 ? 2 * E : E) + c * 32, acc);
       }
       tc::tc_fence_before();
-      tc::mbar_arrive(acc_empty);
+      tc::mbar_arrive_warp(acc_empty);
     }
   }
 
@@ -680,6 +717,7 @@ extern "C" int pfn_attention_bwd_tc(const pfn_attn_desc* d, void* stream) {
   p.dqkv = reinterpret_cast<__nv_bfloat16*>(d->dqkv); p.ld_dqkv = d->ld_dqkv;
   p.lse = d->lse; p.delta = d->delta;
   p.batch_major = d->batch_major;
+  p.trace = nullptr; p.trace_cap = g_trace_cap;
   static bool attr_set = false;
   if (!attr_set) {
     PFN_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
@@ -698,7 +736,9 @@ extern "C" int pfn_attention_bwd_tc(const pfn_attn_desc* d, void* stream) {
     p.n_tiles = (d->T + 127) / 128;
     p.total_work = p.n_tiles * d->B * d->H;
     int grid = num_sms() < p.total_work ? num_sms() : p.total_work;
+    p.trace = g_trace_which == 1 ? g_trace_ptr : nullptr;
     attn_bwd_dq_tc_kernel<<<grid, AB_THREADS, AB_SMEM, s>>>(tmQKV128, tmQKV64, tmDO128, p);
+    p.trace = nullptr;
     PFN_LAUNCH_OK();
   }
   if (d->sep > 0) {

@@ -60,25 +60,6 @@ __device__ __forceinline__ int tile_block_plan(int i0, int sep, int T, int nblk,
   return nblk + nd;
 }
 
-// Debug event trace (CTA 0 only), three private regions (producer / MMA / softmax thread 64) so that logging is a plain
-// store: region r holds [ev, a, b, clock] x cap entries at trace + r*4*cap; counters live in registers of the role.
-struct AttTrace {
-  long long* base; int cap; int n;
-  __device__ __forceinline__ void log(int ev, int a, int b) {
-    if (base != nullptr && n < cap) {
-      long long* e = base + static_cast<size_t>(n) * 4;
-      e[0] = ev; e[1] = a; e[2] = b; e[3] = clock64();
-      ++n;
-    }
-  }
-};
-__device__ __forceinline__ AttTrace att_trace_make(const AttnFwdParams& p, int region) {
-  AttTrace t;
-  t.base = (p.trace != nullptr && blockIdx.x == 0) ? p.trace + static_cast<size_t>(region) * 4 * p.trace_cap : nullptr;
-  t.cap = p.trace_cap; t.n = 0;
-  return t;
-}
-
 __device__ __forceinline__ void load_row128(const __nv_bfloat16* p, float (&v)[32], int chunk) {
   // 32 consecutive bf16 -> fp32 (chunk selects which quarter of the 128-wide row)
   const uint4* src = reinterpret_cast<const uint4*>(p + chunk * 32);
@@ -147,10 +128,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc::mbar_init(&kv_full[s], 1);
       tc::mbar_init(&kv_empty[s], 1);
       tc::mbar_init(&s_full[s], 1);
-      tc::mbar_init(&p_ready[s], 128);
+      tc::mbar_init(&p_ready[s], 4);      // one arrival per softmax warp
     }
     tc::mbar_init(pv_done, 1);
-    tc::mbar_init(o_empty, 128);
+    tc::mbar_init(o_empty, 4);
     tc::mbar_fence_init();
   }
   if (warp == 2) {
@@ -164,9 +145,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int nblk = (p.sep + ATT_BN - 1) / ATT_BN;
 
   if (warp == 0) {
-    // =============================================================== TMA producer
-    if (lane == 0) {
-      AttTrace tr = att_trace_make(p, 0);
+    // =============================================================== TMA producer (converged warp, elected lane issues)
+    {
+      tc::KernelTrace tr = tc::trace_make(p.trace, p.trace_cap, 0);
       uint32_t g = 0;      // running KV-block counter (ring position)
       uint32_t tcount = 0; // running tile counter
       for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
@@ -177,93 +158,105 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         int dstart[2];
         const int nb = tile_block_plan(i0, p.sep, p.T, nblk, dstart);
         tc::mbar_wait(q_empty, (tcount & 1) ^ 1);
-        tr.log(1, tcount, 0);   // Q load issue
-        tc::mbar_expect_tx(q_full, ATT_Q_BYTES);
-        tc::tma_load_3d(sQ, &tmQ, q_full, h * ATT_DH, b, i0);
-        tc::tma_load_3d(sQ + 16384, &tmQ, q_full, h * ATT_DH + 64, b, i0);
+        if (lane == 0) tr.log(1, tcount, 0);   // Q load issue
+        if (tc::elect_one()) {
+          tc::mbar_expect_tx(q_full, ATT_Q_BYTES);
+          tc::tma_load_3d(sQ, &tmQ, q_full, h * ATT_DH, b, i0);
+          tc::tma_load_3d(sQ + 16384, &tmQ, q_full, h * ATT_DH + 64, b, i0);
+        }
+        __syncwarp();
         for (int j = 0; j < nb; ++j, ++g) {
           const int st = g & 1;
           tc::mbar_wait(&kv_empty[st], ((g >> 1) & 1) ^ 1);
-          tr.log(2, tcount, j);   // KV load issue
-          tc::mbar_expect_tx(&kv_full[st], 2 * ATT_KV_BYTES);
+          if (lane == 0) tr.log(2, tcount, j);   // KV load issue
           uint8_t* kdst = sKV + st * 2 * ATT_KV_BYTES;
           uint8_t* vdst = kdst + ATT_KV_BYTES;
           const int j0 = j < nblk ? j * ATT_BN : dstart[j - nblk];
-          tc::tma_load_3d(kdst, &tmKV, &kv_full[st], E + h * ATT_DH, b, j0);
-          tc::tma_load_3d(kdst + 8192, &tmKV, &kv_full[st], E + h * ATT_DH + 64, b, j0);
-          tc::tma_load_3d(vdst, &tmKV, &kv_full[st], 2 * E + h * ATT_DH, b, j0);
-          tc::tma_load_3d(vdst + 8192, &tmKV, &kv_full[st], 2 * E + h * ATT_DH + 64, b, j0);
+          if (tc::elect_one()) {
+            tc::mbar_expect_tx(&kv_full[st], 2 * ATT_KV_BYTES);
+            tc::tma_load_3d(kdst, &tmKV, &kv_full[st], E + h * ATT_DH, b, j0);
+            tc::tma_load_3d(kdst + 8192, &tmKV, &kv_full[st], E + h * ATT_DH + 64, b, j0);
+            tc::tma_load_3d(vdst, &tmKV, &kv_full[st], 2 * E + h * ATT_DH, b, j0);
+            tc::tma_load_3d(vdst + 8192, &tmKV, &kv_full[st], 2 * E + h * ATT_DH + 64, b, j0);
+          }
+          __syncwarp();
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
     // =============================================================== MMA issuer
-    if (lane == 0) {
+    // The whole warp runs the control flow (so addresses / descriptors stay warp-uniform and live in uniform registers);
+    // one elected lane issues the tcgen05 instructions.
+    {
       constexpr uint32_t idesc_qk = tc::umma_idesc_bf16(ATT_BM, ATT_BN, 0, 0);
       constexpr uint32_t idesc_pv = tc::umma_idesc_bf16(ATT_BM, ATT_DH, 0, 1);
       const uint32_t q_addr = tc::smem_u32(sQ);
-      AttTrace tr = att_trace_make(p, 1);
+      tc::KernelTrace tr = tc::trace_make(p.trace, p.trace_cap, 1);
       uint32_t g = 0, tcount = 0;
       auto issue_qk = [&](uint32_t gg) {
         const int st = gg & 1;
         const uint32_t k_addr = tc::smem_u32(sKV + st * 2 * ATT_KV_BYTES);
         const uint32_t d_tmem = tmem_base + (gg & 1) * ATT_BN;
+        if (tc::elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < ATT_DH / 16; ++kk) {
-          const uint64_t a_desc = tc::umma_smem_desc(q_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
-          const uint64_t b_desc = tc::umma_smem_desc(k_addr + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024);
-          tc::umma_bf16_ss(d_tmem, a_desc, b_desc, idesc_qk, kk > 0 ? 1u : 0u);
+          for (int kk = 0; kk < ATT_DH / 16; ++kk) {
+            const uint64_t a_desc = tc::umma_smem_desc(q_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
+            const uint64_t b_desc = tc::umma_smem_desc(k_addr + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024);
+            tc::umma_bf16_ss(d_tmem, a_desc, b_desc, idesc_qk, kk > 0 ? 1u : 0u);
+          }
+          tc::umma_commit(&s_full[gg & 1]);
         }
+        __syncwarp();
       };
       for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
         const int qt = w % p.n_qtiles;
         int dstart[2];
         const int nb = tile_block_plan(qt * ATT_BM, p.sep, p.T, nblk, dstart);
         tc::mbar_wait(q_full, tcount & 1);
-        tr.log(10, tcount, 0);  // Q landed
+        if (lane == 0) tr.log(10, tcount, 0);  // Q landed
         tc::mbar_wait(&kv_full[g & 1], (g >> 1) & 1);
-        tr.log(11, tcount, 0);  // KV0 landed
+        if (lane == 0) tr.log(11, tcount, 0);  // KV0 landed
         tc::tc_fence_after();
         issue_qk(g);
-        tc::umma_commit(&s_full[g & 1]);
         for (int j = 0; j < nb; ++j, ++g) {
           if (j + 1 < nb) {
             const uint32_t gn = g + 1;
             tc::mbar_wait(&kv_full[gn & 1], (gn >> 1) & 1);
-            tr.log(11, tcount, j + 1);
+            if (lane == 0) tr.log(11, tcount, j + 1);
             tc::tc_fence_after();
             issue_qk(gn);
-            tc::umma_commit(&s_full[gn & 1]);
           } else {
-            tc::umma_commit(q_empty);   // every QK^T of this tile has been issued
+            if (tc::elect_one()) tc::umma_commit(q_empty);   // every QK^T of this tile has been issued
+            __syncwarp();
           }
           tc::mbar_wait(&p_ready[g & 1], (g >> 1) & 1);
-          tr.log(12, tcount, j);  // P ready seen by MMA thread
+          if (lane == 0) tr.log(12, tcount, j);  // P ready seen by MMA warp
           if (j == 0) tc::mbar_wait(o_empty, (tcount & 1) ^ 1);
           tc::tc_fence_after();
           const int st = g & 1;
           const uint32_t v_addr = tc::smem_u32(sKV + st * 2 * ATT_KV_BYTES + ATT_KV_BYTES);
           const uint32_t p_tmem = tmem_base + (g & 1) * ATT_BN;
           const uint32_t o_tmem = tmem_base + 128;
+          if (tc::elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < ATT_BN / 16; ++kk) {
-            const uint64_t b_desc = tc::umma_smem_desc(v_addr + kk * 2048, 8192, 1024);
-            tc::umma_bf16_ts(o_tmem, p_tmem + kk * 8, b_desc, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+            for (int kk = 0; kk < ATT_BN / 16; ++kk) {
+              const uint64_t b_desc = tc::umma_smem_desc(v_addr + kk * 2048, 8192, 1024);
+              tc::umma_bf16_ts(o_tmem, p_tmem + kk * 8, b_desc, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+            }
+            tc::umma_commit(&kv_empty[st]);
+            tc::umma_commit(pv_done);
           }
-          tc::umma_commit(&kv_empty[st]);
-          tc::umma_commit(pv_done);
-          tr.log(13, tcount, j);  // PV issued
+          __syncwarp();
+          if (lane == 0) tr.log(13, tcount, j);  // PV issued
         }
       }
     }
-    __syncwarp();
   } else {
     // =============================================================== softmax / correction / epilogue
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    AttTrace tr = att_trace_make(p, 2);
+    tc::KernelTrace tr = tc::trace_make(p.trace, p.trace_cap, 2);
     uint32_t g = 0;
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
       const int bh = w / p.n_qtiles;
@@ -376,7 +369,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc::tmem_st_32x32b_x32(tmem_base + lane_off + buf * ATT_BN, pk);
         tc::tmem_st_wait();
         tc::tc_fence_before();
-        tc::mbar_arrive(&p_ready[buf]);
+        tc::mbar_arrive_warp(&p_ready[buf]);
         if (threadIdx.x == 64) tr.log(21, w, j);   // P published
       }
       // ---- epilogue: O / l, lse   (every valid row has seen at least one key: a train key or itself)
@@ -408,7 +401,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       if (valid) p.lse[static_cast<size_t>(bh) * p.T + i] = (m + log2f(l)) * 0.6931471805599453f;
       tc::tc_fence_before();
-      tc::mbar_arrive(o_empty);
+      tc::mbar_arrive_warp(o_empty);
       if (threadIdx.x == 64) tr.log(23, w, 0);     // epilogue end
     }
   }
@@ -420,9 +413,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tc::tmem_dealloc(tmem_base, 256);
   }
 }
-
-static long long* g_trace_ptr = nullptr;
-static int g_trace_cap = 0;
 
 static int make_qkv_map(CUtensorMap* tm, const void* base, int ld, int width, int B, int T, int box_rows, int batch_major) {
   uint64_t dims[3] = {static_cast<uint64_t>(width), static_cast<uint64_t>(B), static_cast<uint64_t>(T)};
@@ -461,7 +451,7 @@ extern "C" int pfn_attention_fwd_tc(const pfn_attn_desc* d, void* stream) {
   p.n_qtiles = (d->T + ATT_BM - 1) / ATT_BM;
   p.total_work = p.n_qtiles * d->B * d->H;
   p.batch_major = d->batch_major;
-  p.trace = g_trace_ptr;
+  p.trace = g_trace_which == 0 ? g_trace_ptr : nullptr;
   p.trace_cap = g_trace_cap;
   static bool attr_set = false;
   if (!attr_set) {
@@ -473,13 +463,5 @@ extern "C" int pfn_attention_fwd_tc(const pfn_attn_desc* d, void* stream) {
   if (grid > p.total_work) grid = p.total_work;
   attn_fwd_tc_kernel<<<grid, ATT_THREADS, ATT_FWD_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmKV, p);
   PFN_LAUNCH_OK();
-  return 0;
-}
-
-// Debug hook (not part of the product API surface): log clock64 events of CTA 0 of subsequent forward launches into
-// `buf` ([1 + 4*cap] int64, first element = event count; zero it before the launch).  Pass null to switch off.
-extern "C" int pfn_debug_attention_trace(long long* buf, int cap) {
-  g_trace_ptr = buf;
-  g_trace_cap = cap;
   return 0;
 }

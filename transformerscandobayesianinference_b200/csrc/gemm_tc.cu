@@ -99,8 +99,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int total_work = tiles * p.k_splits;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (converged warp, elected lane issues)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
@@ -112,32 +112,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int kb1 = min(kb0 + p.kb_per_split, num_kb_total);
         for (int kb = kb0; kb < kb1; ++kb) {
           tc::mbar_wait(&empty_bar[stage], phase ^ 1);
-          tc::mbar_expect_tx(&full_bar[stage], Cfg::kABytes + Cfg::kBBytes);
           uint8_t* a_dst = sA + stage * Cfg::kABytes;
           uint8_t* b_dst = sB + stage * Cfg::kBBytes;
           const int k0 = kb * kBlockK;
-          if constexpr (!A_MN) {
-            tc::tma_load_2d(a_dst, &tmA, &full_bar[stage], k0, m0);
-          } else {
+          if (tc::elect_one()) {
+            tc::mbar_expect_tx(&full_bar[stage], Cfg::kABytes + Cfg::kBBytes);
+            if constexpr (!A_MN) {
+              tc::tma_load_2d(a_dst, &tmA, &full_bar[stage], k0, m0);
+            } else {
 #pragma unroll
-            for (int c = 0; c < kBlockM / 64; ++c)
-              tc::tma_load_2d(a_dst + c * 8192, &tmA, &full_bar[stage], m0 + c * 64, k0);
-          }
-          if constexpr (!B_MN) {
-            tc::tma_load_2d(b_dst, &tmB, &full_bar[stage], k0, n0);
-          } else {
+              for (int c = 0; c < kBlockM / 64; ++c)
+                tc::tma_load_2d(a_dst + c * 8192, &tmA, &full_bar[stage], m0 + c * 64, k0);
+            }
+            if constexpr (!B_MN) {
+              tc::tma_load_2d(b_dst, &tmB, &full_bar[stage], k0, n0);
+            } else {
 #pragma unroll
-            for (int c = 0; c < BLOCK_N / 64; ++c)
-              tc::tma_load_2d(b_dst + c * 8192, &tmB, &full_bar[stage], n0 + c * 64, k0);
+              for (int c = 0; c < BLOCK_N / 64; ++c)
+                tc::tma_load_2d(b_dst + c * 8192, &tmB, &full_bar[stage], n0 + c * 64, k0);
+            }
           }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (converged warp, elected lane issues)
+    {
       constexpr uint32_t idesc = tc::umma_idesc_bf16(kBlockM, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -156,23 +158,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc::tc_fence_after();
           const uint32_t a_addr = tc::smem_u32(sA + stage * Cfg::kABytes);
           const uint32_t b_addr = tc::smem_u32(sB + stage * Cfg::kBBytes);
+          if (tc::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // K-major: advance 16 elements (32 B) inside the 128 B swizzle row.
-            // MN-major: advance 16 k-rows (16 * 128 B); LBO = stride between 64-wide M/N chunks.
-            const uint64_t a_desc = A_MN ? tc::umma_smem_desc(a_addr + k * 2048, 8192, 1024)
-                                         : tc::umma_smem_desc(a_addr + k * 32, 16, 1024);
-            const uint64_t b_desc = B_MN ? tc::umma_smem_desc(b_addr + k * 2048, 8192, 1024)
-                                         : tc::umma_smem_desc(b_addr + k * 32, 16, 1024);
-            tc::umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              // K-major: advance 16 elements (32 B) inside the 128 B swizzle row.
+              // MN-major: advance 16 k-rows (16 * 128 B); LBO = stride between 64-wide M/N chunks.
+              const uint64_t a_desc = A_MN ? tc::umma_smem_desc(a_addr + k * 2048, 8192, 1024)
+                                           : tc::umma_smem_desc(a_addr + k * 32, 16, 1024);
+              const uint64_t b_desc = B_MN ? tc::umma_smem_desc(b_addr + k * 2048, 8192, 1024)
+                                           : tc::umma_smem_desc(b_addr + k * 32, 16, 1024);
+              tc::umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            tc::umma_commit(&empty_bar[stage]);
+            if (kb == kb1 - 1) tc::umma_commit(&tfull_bar[as]);
           }
-          tc::umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tc::umma_commit(&tfull_bar[as]);
       }
     }
-    __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue warps
     const int ew = warp - 2;
