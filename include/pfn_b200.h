@@ -134,7 +134,8 @@ int pfn_bar_bucket_idx(const float* y, const float* borders, int n_bars, int64_t
  * GP prior sample (reference priors/fast_gp.py:36-58, priors/fast_gp_mix.py:58-134):
  *   K_b = os_b * k(x_b, x_b; ls_b) + noise_b * I ;  L_b = chol(K_b) ;  y_b = L_b z_b
  * x [Bn, T, F] fp32, z [Bn, T] fp32, ls [Bn, F], os [Bn], noise [Bn] fp32, y [Bn, T] fp32,
- * work [Bn, T, T] fp32 scratch (holds L on return), info [Bn] int (0 ok, k>0: pivot k not positive).
+ * work [Bn, T, ldw] fp32 scratch, ldw = T rounded up to 4; on return work[b][c][r] = L_b[r][c] (the factor, TRANSPOSED;
+ * entries with r < c are unspecified), info [Bn] int (0 ok, k>0: pivot k not positive).
  * jitter is added to every diagonal (gpytorch psd_safe_cholesky retry semantics are driven by the host).
  * ---------------------------------------------------------------------------------------------- */
 int pfn_gp_sample(const float* x, const float* z, const float* ls, const float* os, const float* noise, float jitter,

@@ -145,7 +145,7 @@ def test_gp_sample_matches_lapack(cuda_device, kernel, code, Bn, T, F, noise):
     L.gp_sample(x, z, ls, os_, nz, 0.0, code, y, work, info)
     yr, Lr = O.gp_sample_ref(x.cpu().double(), z.cpu().double(), ls.cpu().double(), os_.cpu().double(), nz.cpu().double(), kernel)
     assert info.tolist() == [0] * Bn
-    Lg = torch.tril(work[:, :, :T].cpu().double())
+    Lg = torch.tril(work[:, :, :T].transpose(1, 2).cpu().double())     # the kernel keeps the factor transposed
     K = O.gp_kernel_ref(x.cpu().double(), ls.cpu().double(), os_.cpu().double(), nz.cpu().double(), kernel)
     resid = (Lg @ Lg.transpose(-1, -2) - K).abs().max().item()
     assert resid <= 2e-5 * K.abs().max().item(), f"L L^T residual {resid}"

@@ -10,7 +10,9 @@
 //     L11      = chol(U[c0:c0+32, :])                                     (one warp, rows in registers, shuffles)
 //     L[r, c0:c0+32] = U[r, :] L11^-T  for r > c0+31                      (one thread per row, L11 broadcast from smem)
 //     y[r]    += L[r, c0:c0+32] . z[c0:c0+32]
-// K is never materialised; the only HBM traffic is writing L once and re-reading finished panels.
+// K is never materialised; the only HBM traffic is writing the factor once and re-reading finished panels.
+// The factor is kept TRANSPOSED in `work` (work[b][c][r] = L[r][c]): panel re-reads become contiguous rows that stream
+// through a 3-stage cp.async ring straight into the k-major smem tiles, and the panel write-back is coalesced.
 #include "common.cuh"
 #include "../../include/pfn_b200.h"
 
@@ -19,6 +21,15 @@ namespace pfn {
 constexpr int NB = 32;        // panel width
 constexpr int TR = 128;       // rows per update tile
 constexpr int GP_MAX_F = 128;
+constexpr int GP_STAGES = 3;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  const int bytes = valid ? 16 : 0;   // src-size 0 => zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ float gp_kernel_value(float d2, float os, int kernel_type) {
   if (kernel_type == PFN_KERNEL_RBF) return os * expf(-0.5f * d2);
@@ -36,8 +47,9 @@ __global__ void __launch_bounds__(256, 2)
 gp_sample_kernel(const float* __restrict__ x, const float* __restrict__ z, const float* __restrict__ ls,
                  const float* __restrict__ os_arr, const float* __restrict__ noise_arr, float jitter, int kernel_type,
                  float* __restrict__ y, float* work, int* __restrict__ info, int T, int F, int ldw) {
-  __shared__ __align__(16) float sR[NB][TR];        // sR[k][r]  = L[r0 + r, j0 + k]
-  __shared__ __align__(16) float sC[NB][NB];        // sC[k][c]  = L[c0 + c, j0 + k]
+  extern __shared__ __align__(16) float gp_dyn[];         // the cp.async ring lives in dynamic shared memory (60 KB)
+  float (*sR)[NB][TR] = reinterpret_cast<float (*)[NB][TR]>(gp_dyn);                              // sR[s][k][r] = L[r0 + r, j0 + k]
+  float (*sC)[NB][NB] = reinterpret_cast<float (*)[NB][NB]>(gp_dyn + GP_STAGES * NB * TR);        // sC[s][k][c] = L[c0 + c, j0 + k]
   __shared__ float sU[TR][NB + 1];                  // updated tile, row-major (padded)
   __shared__ __align__(16) float sL[NB][NB];        // L11 (row-major), unit rows past the matrix edge
   __shared__ float sLinv[NB];
@@ -51,7 +63,7 @@ gp_sample_kernel(const float* __restrict__ x, const float* __restrict__ z, const
   const float* xb = x + static_cast<size_t>(b) * T * F;
   const float* zb = z + static_cast<size_t>(b) * T;
   float* yb = y + static_cast<size_t>(b) * T;
-  float* Lb = work + static_cast<size_t>(b) * T * ldw;
+  float* Lt = work + static_cast<size_t>(b) * T * ldw;   // Lt[c * ldw + r] = L[r][c]
   const float os = os_arr[b];
   const float diag_add = noise_arr[b] + jitter;
 
@@ -73,35 +85,40 @@ gp_sample_kernel(const float* __restrict__ x, const float* __restrict__ z, const
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-      for (int j0 = 0; j0 < c0; j0 += NB) {
-        {
-          const int row = tid & (TR - 1);
-          const int half = tid >> 7;
-          const int r = r0 + row;
-          if (r < T) {
-            const float4* src = reinterpret_cast<const float4*>(Lb + static_cast<size_t>(r) * ldw + j0 + half * 16);
+      // 3-stage cp.async ring over the 32-column chunks of the finished panels (rows of Lt are contiguous in r)
+      const int nch = c0 / NB;
+      auto issue = [&](int ch) {
+        const int st = ch % GP_STAGES;
+        const int j0 = ch * NB;
+        // sR: 32 k-rows x 128 floats = 1024 16-byte pieces; sC: 32 x 32 floats = 256 pieces; 5 per thread
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 v = src[q];
-              sR[half * 16 + 4 * q + 0][row] = v.x;
-              sR[half * 16 + 4 * q + 1][row] = v.y;
-              sR[half * 16 + 4 * q + 2][row] = v.z;
-              sR[half * 16 + 4 * q + 3][row] = v.w;
-            }
-          } else {
-#pragma unroll
-            for (int q = 0; q < 16; ++q) sR[half * 16 + q][row] = 0.f;
-          }
-          const int c = tid & 31, kq = tid >> 5;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (c0 + c < T) v = *reinterpret_cast<const float4*>(Lb + static_cast<size_t>(c0 + c) * ldw + j0 + kq * 4);
-          sC[kq * 4 + 0][c] = v.x; sC[kq * 4 + 1][c] = v.y; sC[kq * 4 + 2][c] = v.z; sC[kq * 4 + 3][c] = v.w;
+        for (int q = 0; q < 4; ++q) {
+          const int piece = tid + q * 256;
+          const int k = piece >> 5, r4 = (piece & 31) * 4;
+          const int r = r0 + r4;
+          cp_async16(&sR[st][k][r4], Lt + static_cast<size_t>(j0 + k) * ldw + r, r < ldw);
         }
+        {
+          const int k = tid >> 3, c4 = (tid & 7) * 4;
+          const int c = c0 + c4;
+          cp_async16(&sC[st][k][c4], Lt + static_cast<size_t>(j0 + k) * ldw + c, c < ldw);
+        }
+      };
+#pragma unroll
+      for (int sidx = 0; sidx < GP_STAGES - 1; ++sidx) {
+        if (sidx < nch) issue(sidx);
+        cp_async_commit();
+      }
+      for (int ch = 0; ch < nch; ++ch) {
+        cp_async_wait<GP_STAGES - 2>();
         __syncthreads();
+        if (ch + GP_STAGES - 1 < nch) issue(ch + GP_STAGES - 1);
+        cp_async_commit();
+        const int st = ch % GP_STAGES;
 #pragma unroll
         for (int k = 0; k < NB; ++k) {
-          const float4 a = *reinterpret_cast<const float4*>(&sR[k][ty * 4]);
-          const float4 bb = *reinterpret_cast<const float4*>(&sC[k][tx * 4]);
+          const float4 a = *reinterpret_cast<const float4*>(&sR[st][k][ty * 4]);
+          const float4 bb = *reinterpret_cast<const float4*>(&sC[st][k][tx * 4]);
           const float av[4] = {a.x, a.y, a.z, a.w};
           const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
@@ -109,8 +126,9 @@ gp_sample_kernel(const float* __restrict__ x, const float* __restrict__ z, const
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
         }
-        __syncthreads();
       }
+      cp_async_wait<0>();
+      __syncthreads();     // every thread is done with the ring before the next tile refills it
       // ---------------------------------------------------------------- U = K - acc   (kernel built on the fly)
       {
         float d2[4][4];
@@ -206,10 +224,9 @@ gp_sample_kernel(const float* __restrict__ x, const float* __restrict__ z, const
 #pragma unroll
           for (int c = 0; c < NB; ++c) dot = fmaf(v[c], sz[c], dot);
           yb[r] += dot;
-          float* dst = Lb + static_cast<size_t>(r) * ldw + c0;
 #pragma unroll
-          for (int c = 0; c < NB; c += 4) {
-            if (c0 + c < ldw) *reinterpret_cast<float4*>(dst + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+          for (int c = 0; c < NB; ++c) {
+            if (c0 + c < T) Lt[static_cast<size_t>(c0 + c) * ldw + r] = v[c];     // lanes = consecutive r: coalesced
           }
         }
       }
@@ -231,7 +248,13 @@ extern "C" int pfn_gp_sample(const float* x, const float* z, const float* ls, co
   PFN_CHECK_ARG(kernel_type >= PFN_KERNEL_RBF && kernel_type <= PFN_KERNEL_MATERN52, "gp_sample: bad kernel type %d", kernel_type);
   PFN_CHECK_ARG((reinterpret_cast<uintptr_t>(work) & 15) == 0, "gp_sample: work buffer must be 16-byte aligned");
   const int ldw = (T + 3) & ~3;
-  gp_sample_kernel<<<Bn, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, z, ls, os, noise, jitter, kernel_type, y,
+  constexpr int kDynSmem = GP_STAGES * (NB * TR + NB * NB) * static_cast<int>(sizeof(float));
+  static bool attr_set = false;
+  if (!attr_set) {
+    PFN_CUDA_OK(cudaFuncSetAttribute(gp_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem));
+    attr_set = true;
+  }
+  gp_sample_kernel<<<Bn, 256, kDynSmem, reinterpret_cast<cudaStream_t>(stream)>>>(x, z, ls, os, noise, jitter, kernel_type, y,
                                                                          work, info, T, F, ldw);
   PFN_LAUNCH_OK();
   return 0;

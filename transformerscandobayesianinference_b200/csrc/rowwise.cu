@@ -315,12 +315,58 @@ __global__ void layernorm_bwd_generic(const T* dh, int lddh, const T* z, int ldz
 }
 
 // --------------------------------------------------------------------------------------------
-// Column sums
+// Column sums.  Vector path: one warp streams whole rows with 16 B loads (lane owns 8 consecutive columns per
+// 256-column group), accumulates in registers over the rows it owns, CTA combines in shared memory, one atomicAdd
+// per column per CTA.  Generic path: one thread per column.
 // --------------------------------------------------------------------------------------------
+template <typename T, int NV>
+__global__ void __launch_bounds__(256)
+colsum_vec_kernel(const T* __restrict__ X0, int ld, float* __restrict__ out0, int rows, int N0) {
+  extern __shared__ float sred[];   // [N]
+  // blockIdx.y selects a group of NV*256 columns
+  const int col_base = blockIdx.y * NV * 256;
+  const T* X = X0 + col_base;
+  float* out = out0 + col_base;
+  const int N = min(N0 - col_base, NV * 256);
+  const int lane = threadIdx.x & 31;
+  const int warps_per_cta = blockDim.x >> 5;
+  const int warp = blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * warps_per_cta;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) sred[i] = 0.f;
+  __syncthreads();
+  float acc[NV][8];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[v][i] = 0.f;
+  for (int row = warp; row < rows; row += nwarps) {
+    const T* xr = X + static_cast<size_t>(row) * ld;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int col = (v * 32 + lane) * 8;
+      if (col < N) {
+        float x[8];
+        load8<T>(xr + col, x);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[v][i] += x[i];
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int col = (v * 32 + lane) * 8;
+    if (col < N) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(&sred[col + i], acc[v][i]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < N; i += blockDim.x) atomicAdd(&out[i], sred[i]);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const T* __restrict__ X, int ld, float* __restrict__ out, int rows, int N, int rows_per_cta) {
-  // threads: 32 column-groups (x) by 8 row-lanes (y); each x-thread covers 8 consecutive columns when aligned
   const int col = blockIdx.y * blockDim.x + threadIdx.x;
   const int r_begin = blockIdx.x * rows_per_cta;
   const int r_end = min(r_begin + rows_per_cta, rows);
@@ -442,14 +488,35 @@ extern "C" int pfn_layernorm_bwd(const void* dh, int lddh, const void* z, int ld
   return layernorm_bwd_dispatch<__nv_bfloat16>(dh, lddh, z, ldz, mean, rstd, gamma, dz, lddz, dgamma, dbeta, colsum_out, rows, E, s);
 }
 
+template <typename T>
+static int colsum_dispatch(const void* X, int ld, float* out, int rows, int N, cudaStream_t s) {
+  const T* xp = reinterpret_cast<const T*>(X);
+  const bool vec = (N % 8 == 0) && (ld % 8 == 0) && (reinterpret_cast<uintptr_t>(X) & 15) == 0;
+  if (vec) {
+    int gx = num_sms() * 4;
+    const int max_grid = (rows + 7) / 8;
+    if (gx > max_grid) gx = max_grid;
+    if (N <= 256) colsum_vec_kernel<T, 1><<<gx, 256, 256 * sizeof(float), s>>>(xp, ld, out, rows, N);
+    else if (N <= 512) colsum_vec_kernel<T, 2><<<gx, 256, 512 * sizeof(float), s>>>(xp, ld, out, rows, N);
+    else {
+      const int groups = (N + 1023) / 1024;            // 1024 columns (NV = 4) per blockIdx.y
+      int gxx = gx / groups > 0 ? (gx * 2) / groups : 1;
+      if (gxx > max_grid) gxx = max_grid;
+      colsum_vec_kernel<T, 4><<<dim3(gxx, groups), 256, 1024 * sizeof(float), s>>>(xp, ld, out, rows, N);
+    }
+  } else {
+    int rows_per_cta = (rows + num_sms() * 2 - 1) / (num_sms() * 2);
+    if (rows_per_cta < 64) rows_per_cta = 64;
+    dim3 grid((rows + rows_per_cta - 1) / rows_per_cta, (N + 255) / 256);
+    colsum_kernel<T><<<grid, 256, 0, s>>>(xp, ld, out, rows, N, rows_per_cta);
+  }
+  PFN_LAUNCH_OK();
+  return 0;
+}
+
 extern "C" int pfn_colsum(const void* X, int ld, int dtype, float* out, int rows, int N, void* stream) {
   PFN_CHECK_ARG(rows > 0 && N > 0, "colsum: bad shape rows=%d N=%d", rows, N);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  int rows_per_cta = (rows + num_sms() * 2 - 1) / (num_sms() * 2);
-  if (rows_per_cta < 64) rows_per_cta = 64;
-  dim3 grid((rows + rows_per_cta - 1) / rows_per_cta, (N + 255) / 256);
-  if (dtype == PFN_F32) colsum_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(X), ld, out, rows, N, rows_per_cta);
-  else colsum_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(X), ld, out, rows, N, rows_per_cta);
-  PFN_LAUNCH_OK();
-  return 0;
+  if (dtype == PFN_F32) return colsum_dispatch<float>(X, ld, out, rows, N, s);
+  return colsum_dispatch<__nv_bfloat16>(X, ld, out, rows, N, s);
 }

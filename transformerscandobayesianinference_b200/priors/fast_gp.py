@@ -44,7 +44,7 @@ def sample_gp(x, z, lengthscale, outputscale, noise, kernel_type=L.KERNEL_RBF, r
     for jitter in _JITTERS:
         L.gp_sample(x, z, lengthscale, outputscale, noise, jitter, kernel_type, y, work, info)
         if not bool(info.any().item()):
-            return (y, work[:, :, :T]) if return_factor else y
+            return (y, torch.tril(work[:, :, :T].transpose(1, 2))) if return_factor else y
     raise NotPSDError(f"kernel matrix not positive definite even with jitter {_JITTERS[-1]:g} "
                       f"(first failing pivots: {info[info > 0][:8].tolist()})")
 
