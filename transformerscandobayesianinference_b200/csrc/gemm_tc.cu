@@ -13,7 +13,8 @@
 // Structure (one CTA per SM, persistent over work items = output tile x k-split):
 //   warp 0      : TMA producer   (cp.async.bulk.tensor, 128B swizzle, mbarrier complete_tx)
 //   warp 1      : MMA issuer     (one lane issues tcgen05.mma 128 x BLOCK_N x 16, commits to mbarriers)
-//   warps 2..9  : epilogue       (tcgen05.ld TMEM->regs, bias / GELU / residual / GELU' , global stores)
+//   warps 2..9  : epilogue       (tcgen05.ld TMEM->regs, bias / GELU / residual / GELU'; bf16 tiles are staged in
+//                                 128B-swizzled smem and written with TMA stores, fp32/atomic outputs go direct)
 //   TMEM        : 2 accumulator stages x BLOCK_N fp32 columns (epilogue of tile i overlaps MMA of i+1)
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -36,6 +37,7 @@ struct GemmTcParams {
   int k_splits;
   int kb_per_split;              // k-blocks (of 64) per split
   int tiles_m, tiles_n;
+  int tma_store;                 // 1 => bf16 C (and C2) leave through the smem staging buffer + TMA store
 };
 
 constexpr int kBlockM = 128;
@@ -45,25 +47,32 @@ constexpr int kNumThreads = 64 + kNumEpiWarps * 32;
 
 template <int BLOCK_N>
 struct GemmCfg {
-  static constexpr int kStages = BLOCK_N == 256 ? 4 : 6;
+  static constexpr int kStagesMax = BLOCK_N == 256 ? 4 : 6;      // fp32 / atomic outputs: no staging buffer, deeper ring
+  static constexpr int kStagesStaged = BLOCK_N == 256 ? 3 : 5;   // bf16 outputs: one stage gives way to the staging buffer
   static constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kTmemCols = 2 * BLOCK_N;
-  static constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + 256 + 1024;
+  static constexpr int kStageOutBytes = kBlockM * BLOCK_N * 2;   // bf16 output tile (two column halves, one per epilogue group)
+  static constexpr int kRingBytes = kStagesMax * (kABytes + kBBytes);
+  static constexpr int kStagedBytes = kStagesStaged * (kABytes + kBBytes) + kStageOutBytes;
+  static constexpr int kDataBytes = kRingBytes > kStagedBytes ? kRingBytes : kStagedBytes;
+  static constexpr int kSmemBytes = kDataBytes + 256 + 1024;
 };
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kNumThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const GemmTcParams p) {
   using Cfg = GemmCfg<BLOCK_N>;
-  constexpr int STAGES = Cfg::kStages;
+  const int STAGES = p.tma_store ? Cfg::kStagesStaged : Cfg::kStagesMax;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * Cfg::kABytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * (Cfg::kABytes + Cfg::kBBytes));
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint8_t* sOut = smem + STAGES * (Cfg::kABytes + Cfg::kBBytes);      // only used when p.tma_store
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kDataBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStagesMax;
+  uint64_t* tfull_bar = empty_bar + Cfg::kStagesMax;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
@@ -73,6 +82,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tmA);
     tc::tma_prefetch_desc(&tmB);
+    if (p.tma_store) { tc::tma_prefetch_desc(&tmC); if (p.C2 != nullptr) tc::tma_prefetch_desc(&tmC2); }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -179,10 +189,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
+    // Two groups of four warps; group `half` owns the left / right BLOCK_N/2 columns of the tile and its own staging
+    // buffer ([128 rows x 64 cols] bf16 chunks in the TMA 128-byte swizzle).
     const int ew = warp - 2;
     const int q = warp & 3;              // TMEM lane quarter this warp may access
     const int half = ew >> 2;            // column half
-    constexpr int COLS_PER_WARP = BLOCK_N / 2;
+    constexpr int COLS_PER_GROUP = BLOCK_N / 2;
+    constexpr int OUT_CHUNKS = COLS_PER_GROUP / 64;
+    uint8_t* stg = sOut + half * (Cfg::kStageOutBytes / 2);
+    const bool issuer = (ew & 3) == 0 && lane == 0;       // the one thread per group that owns the bulk-store groups
+    const int nbar = 1 + half;                             // named barrier of this group (0 is __syncthreads)
+    const bool two_pass = p.tma_store && p.act == PFN_EPI_GELU && p.C2 != nullptr;
+    bool store_pending = false;
     int it = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
       const int split = w / tiles;
@@ -193,127 +211,161 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t aphase = (it >> 1) & 1;
       tc::mbar_wait(&tfull_bar[as], aphase);
       tc::tc_fence_after();
-      const int row = m0 + q * 32 + lane;
+      const int trow = q * 32 + lane;
+      const int row = m0 + trow;
       const bool row_ok = row < p.M;
       const bool add_bias = p.bias != nullptr && split == 0;
+      const int npass = two_pass ? 2 : 1;
 #pragma unroll 1
-      for (int cc = 0; cc < COLS_PER_WARP; cc += 32) {
-        const int col0 = n0 + half * COLS_PER_WARP + cc;
-        if (col0 >= p.N) break;  // warp-uniform
-        uint32_t v[32];
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                               static_cast<uint32_t>(as * BLOCK_N + half * COLS_PER_WARP + cc);
-        tc::tmem_ld_32x32b_x32(taddr, v);
-        tc::tmem_ld_wait();
-        float f[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-        const bool full_chunk = (col0 + 32 <= p.N);
-        if (add_bias) {
-          if (full_chunk) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
-              f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (col0 + i < p.N) f[i] += __ldg(p.bias + col0 + i);
-          }
+      for (int pass = 0; pass < npass; ++pass) {
+        // pass 0 of a two-pass tile writes the pre-activation (C2), the last pass writes C
+        const bool write_pre_only = two_pass && pass == 0;
+        if (p.tma_store && store_pending) {
+          // the previous bulk store must have finished READING the staging buffer before it is overwritten
+          if (issuer) tc::tma_store_wait_read<0>();
+          asm volatile("bar.sync %0, 128;" ::"r"(nbar) : "memory");
+          store_pending = false;
         }
-        if (p.act == PFN_EPI_GELU) {
-          if (p.C2 != nullptr && row_ok) {
-            __nv_bfloat16* dst = p.C2 + static_cast<size_t>(row) * p.ldc2 + col0;
+#pragma unroll 1
+        for (int cc = 0; cc < COLS_PER_GROUP; cc += 32) {
+          const int col0 = n0 + half * COLS_PER_GROUP + cc;
+          if (col0 >= p.N) break;  // warp-uniform
+          uint32_t v[32];
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                 static_cast<uint32_t>(as * BLOCK_N + half * COLS_PER_GROUP + cc);
+          tc::tmem_ld_32x32b_x32(taddr, v);
+          tc::tmem_ld_wait();
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          const bool full_chunk = (col0 + 32 <= p.N);
+          if (add_bias) {
+            if (full_chunk) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+                f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < p.N) f[i] += __ldg(p.bias + col0 + i);
+            }
+          }
+          if (p.act == PFN_EPI_GELU && !write_pre_only) {
+            if (p.C2 != nullptr && row_ok && !p.tma_store) {
+              __nv_bfloat16* dst = p.C2 + static_cast<size_t>(row) * p.ldc2 + col0;
+              if (full_chunk) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                  uint4 pk;
+                  pk.x = tc::pack_bf16x2(f[i], f[i + 1]); pk.y = tc::pack_bf16x2(f[i + 2], f[i + 3]);
+                  pk.z = tc::pack_bf16x2(f[i + 4], f[i + 5]); pk.w = tc::pack_bf16x2(f[i + 6], f[i + 7]);
+                  *reinterpret_cast<uint4*>(dst + i) = pk;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (col0 + i < p.N) dst[i] = __float2bfloat16_rn(f[i]);
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
+          }
+          if (p.aux != nullptr && row_ok && !write_pre_only && (p.act == PFN_EPI_GELU_BWD || split == 0)) {
+            const __nv_bfloat16* src = p.aux + static_cast<size_t>(row) * p.ld_aux + col0;
+            float a[32];
             if (full_chunk) {
 #pragma unroll
               for (int i = 0; i < 32; i += 8) {
-                uint4 pk;
-                __nv_bfloat162 t0 = __floats2bfloat162_rn(f[i], f[i + 1]);
-                __nv_bfloat162 t1 = __floats2bfloat162_rn(f[i + 2], f[i + 3]);
-                __nv_bfloat162 t2 = __floats2bfloat162_rn(f[i + 4], f[i + 5]);
-                __nv_bfloat162 t3 = __floats2bfloat162_rn(f[i + 6], f[i + 7]);
-                pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-                pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-                *reinterpret_cast<uint4*>(dst + i) = pk;
+                const uint4 pk = *reinterpret_cast<const uint4*>(src + i);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 t = __bfloat1622float2(h[j]);
+                  a[i + 2 * j] = t.x; a[i + 2 * j + 1] = t.y;
+                }
               }
             } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (col0 + i < p.N) dst[i] = __float2bfloat16_rn(f[i]);
+              for (int i = 0; i < 32; ++i) a[i] = (col0 + i < p.N) ? __bfloat162float(src[i]) : 0.f;
+            }
+            if (p.act == PFN_EPI_GELU_BWD) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] *= gelu_erf_grad(a[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] += a[i];
             }
           }
+          if (p.tma_store) {
+            // staging write: 64-column chunk (cc / 64), 16-byte units (cc % 64) / 8 .. +3 of row `trow`, XOR-swizzled
+            uint8_t* rowp = stg + (cc >> 6) * 16384 + trow * 128;
+            const int u0 = (cc & 63) >> 3;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
+            for (int i = 0; i < 4; ++i) {
+              uint4 pk;
+              pk.x = tc::pack_bf16x2(f[8 * i], f[8 * i + 1]); pk.y = tc::pack_bf16x2(f[8 * i + 2], f[8 * i + 3]);
+              pk.z = tc::pack_bf16x2(f[8 * i + 4], f[8 * i + 5]); pk.w = tc::pack_bf16x2(f[8 * i + 6], f[8 * i + 7]);
+              *reinterpret_cast<uint4*>(rowp + (((u0 + i) ^ (trow & 7)) << 4)) = pk;
+            }
+          } else if (row_ok) {
+            if (p.c_f32) {
+              float* dst = reinterpret_cast<float*>(p.C) + static_cast<size_t>(row) * p.ldc + col0;
+              if (p.accumulate) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (col0 + i < p.N) atomicAdd(dst + i, f[i]);
+              } else if (full_chunk) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                  *reinterpret_cast<float4*>(dst + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (col0 + i < p.N) dst[i] = f[i];
+              }
+            } else {
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<size_t>(row) * p.ldc + col0;
+              if (full_chunk) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                  uint4 pk;
+                  pk.x = tc::pack_bf16x2(f[i], f[i + 1]); pk.y = tc::pack_bf16x2(f[i + 2], f[i + 3]);
+                  pk.z = tc::pack_bf16x2(f[i + 4], f[i + 5]); pk.w = tc::pack_bf16x2(f[i + 6], f[i + 7]);
+                  *reinterpret_cast<uint4*>(dst + i) = pk;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (col0 + i < p.N) dst[i] = __float2bfloat16_rn(f[i]);
+              }
+            }
+          }
         }
-        if (p.aux != nullptr && row_ok && (p.act == PFN_EPI_GELU_BWD || split == 0)) {
-          const __nv_bfloat16* src = p.aux + static_cast<size_t>(row) * p.ld_aux + col0;
-          float a[32];
-          if (full_chunk) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              const uint4 pk = *reinterpret_cast<const uint4*>(src + i);
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 t = __bfloat1622float2(h[j]);
-                a[i + 2 * j] = t.x; a[i + 2 * j + 1] = t.y;
-              }
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) a[i] = (col0 + i < p.N) ? __bfloat162float(src[i]) : 0.f;
-          }
-          if (p.act == PFN_EPI_GELU_BWD) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] *= gelu_erf_grad(a[i]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] += a[i];
-          }
+        if (pass == npass - 1) {
+          // accumulator stage drained: hand it back to the MMA warp
+          tc::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&tempty_bar[as]);
         }
-        if (row_ok) {
-          if (p.c_f32) {
-            float* dst = reinterpret_cast<float*>(p.C) + static_cast<size_t>(row) * p.ldc + col0;
-            if (p.accumulate) {
+        if (p.tma_store) {
+          tc::fence_proxy_async_smem();                       // generic-proxy staging writes -> visible to the TMA
+          asm volatile("bar.sync %0, 128;" ::"r"(nbar) : "memory");
+          if (issuer) {
+            const CUtensorMap* tm = write_pre_only ? &tmC2 : &tmC;
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (col0 + i < p.N) atomicAdd(dst + i, f[i]);
-            } else if (full_chunk) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 4)
-                *reinterpret_cast<float4*>(dst + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (col0 + i < p.N) dst[i] = f[i];
+            for (int c = 0; c < OUT_CHUNKS; ++c) {
+              const int cbase = n0 + half * COLS_PER_GROUP + c * 64;
+              if (cbase < p.N) tc::tma_store_2d(tm, stg + c * 16384, cbase, m0);   // rows >= M / cols >= N are clipped
             }
-          } else {
-            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<size_t>(row) * p.ldc + col0;
-            if (full_chunk) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 8) {
-                uint4 pk;
-                __nv_bfloat162 t0 = __floats2bfloat162_rn(f[i], f[i + 1]);
-                __nv_bfloat162 t1 = __floats2bfloat162_rn(f[i + 2], f[i + 3]);
-                __nv_bfloat162 t2 = __floats2bfloat162_rn(f[i + 4], f[i + 5]);
-                __nv_bfloat162 t3 = __floats2bfloat162_rn(f[i + 6], f[i + 7]);
-                pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-                pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-                *reinterpret_cast<uint4*>(dst + i) = pk;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (col0 + i < p.N) dst[i] = __float2bfloat16_rn(f[i]);
-            }
+            tc::tma_store_commit();
           }
+          store_pending = true;
         }
       }
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&tempty_bar[as]);
     }
+    if (p.tma_store && issuer) tc::tma_store_wait<0>();        // all bulk stores complete before the CTA exits
   }
 
   tc::tc_fence_before();
@@ -340,7 +392,24 @@ static int launch_gemm_tc(const pfn_gemm_desc* d, cudaStream_t stream) {
     strides[1] = static_cast<uint64_t>(d->ldb) * 2;
     if (int rc = make_tensor_map_bf16(&tmB, d->B, 2, dims, strides, box, true)) return rc;
   }
+  CUtensorMap tmC, tmC2;
+  memset(&tmC, 0, sizeof(tmC));
+  memset(&tmC2, 0, sizeof(tmC2));
+  // bf16 outputs without accumulation leave through smem staging + TMA store (needs 16 B aligned rows)
+  const bool tma_store = d->c_dtype == PFN_BF16 && !d->accumulate && (d->k_splits <= 1) && d->ldc % 8 == 0 &&
+                         (d->C2 == nullptr || d->ldc2 % 8 == 0);
+  if (tma_store) {
+    uint64_t dims[2] = {static_cast<uint64_t>(d->N), static_cast<uint64_t>(d->M)};
+    uint64_t strides[2] = {0, static_cast<uint64_t>(d->ldc) * 2};
+    uint32_t box[2] = {64, kBlockM};
+    if (int rc = make_tensor_map_bf16(&tmC, d->C, 2, dims, strides, box, true)) return rc;
+    if (d->C2 != nullptr) {
+      strides[1] = static_cast<uint64_t>(d->ldc2) * 2;
+      if (int rc = make_tensor_map_bf16(&tmC2, d->C2, 2, dims, strides, box, true)) return rc;
+    }
+  }
   GemmTcParams p;
+  p.tma_store = tma_store ? 1 : 0;
   p.M = d->M; p.N = d->N; p.K = d->K;
   p.bias = d->bias;
   p.aux = reinterpret_cast<const __nv_bfloat16*>(d->aux);
@@ -367,7 +436,7 @@ static int launch_gemm_tc(const pfn_gemm_desc* d, cudaStream_t stream) {
     PFN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  kern<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  kern<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, tmC2, p);
   PFN_LAUNCH_OK();
   return 0;
 }
