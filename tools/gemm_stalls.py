@@ -1,0 +1,22 @@
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from transformerscandobayesianinference_b200 import _lib as L
+dev = torch.device("cuda:0")
+N = 512000
+for (M, Nn, K, amn, bmn, name) in [(N, 1536, 512, 0, 0, "qkv fwd"), (N, 512, 512, 0, 0, "out fwd"), (N, 512, 1536, 0, 1, "qkv dgrad"), (1536, 512, N, 1, 1, "qkv wgrad")]:
+    A = torch.randn((K, M) if amn else (M, K), device=dev).to(torch.bfloat16)
+    Bm = torch.randn((K, Nn) if bmn else (Nn, K), device=dev).to(torch.bfloat16)
+    wg = amn and bmn
+    C = torch.zeros(M, Nn, device=dev, dtype=torch.float32 if wg else torch.bfloat16)
+    run = lambda: L.gemm(A, Bm, C, a_mn_major=bool(amn), b_mn_major=bool(bmn), M=M, N=Nn, K=K, accumulate=wg, k_splits=37 if wg else 1, use_tc=True)
+    for _ in range(3): run()
+    buf = torch.zeros(148 * 4, device=dev, dtype=torch.int64)
+    L.load().pfn_debug_attention_trace(buf.data_ptr(), 0, 10)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); run(); e1.record(); torch.cuda.synchronize()
+    L.load().pfn_debug_attention_trace(None, 0, 0)
+    st = buf.view(148, 4).double().mean(0).tolist()
+    ms = e0.elapsed_time(e1)
+    print(f"{name}: {ms:.3f} ms | mean clocks per CTA waiting: producer(empty) {st[0]:.0f}, MMA(full) {st[1]:.0f}, MMA(tempty) {st[2]:.0f}, epilogue(tfull) {st[3]:.0f}")

@@ -41,6 +41,17 @@ if what in ("gemm", "all"):
             t = timeit(lambda: L.gemm(A, Bm, C, a_mn_major=bool(amn), b_mn_major=bool(bmn), M=M, N=Nn, K=K, accumulate=wg, k_splits=splits, use_tc=True))
             print(f"gemm {name} {M}x{Nn}x{K} splits={splits}: {t:.3f} ms ({2 * M * Nn * K / t / 1e9:.0f} TF/s)", flush=True)
         del A, Bm, C
+if what in ("gemmepi", "all"):
+    N = 512000
+    x = torch.randn(N, 512, device=dev).to(torch.bfloat16); w1 = (torch.randn(1024, 512, device=dev) * .05).to(torch.bfloat16)
+    g = torch.empty(N, 1024, device=dev, dtype=torch.bfloat16); u = torch.empty_like(g); b1 = torch.randn(1024, device=dev)
+    t = timeit(lambda: L.gemm(x, w1, g, bias=b1, C2=u, epilogue=L.EPI_GELU, use_tc=True)); print(f"mlp1 fwd bias+GELU+C2: {t:.3f} ms ({2*N*1024*512/t/1e9:.0f} TF/s)")
+    w2 = (torch.randn(512, 1024, device=dev) * .05).to(torch.bfloat16); z = torch.empty(N, 512, device=dev, dtype=torch.bfloat16); b2 = torch.randn(512, device=dev)
+    t = timeit(lambda: L.gemm(g, w2, z, bias=b2, aux=x, use_tc=True)); print(f"mlp2 fwd bias+residual: {t:.3f} ms ({2*N*1024*512/t/1e9:.0f} TF/s)")
+    du = torch.empty_like(u)
+    t = timeit(lambda: L.gemm(z, w2, du, b_mn_major=True, aux=u, epilogue=L.EPI_GELU_BWD, M=N, N=1024, K=512, use_tc=True)); print(f"mlp2 dgrad * GELU'(u): {t:.3f} ms ({2*N*1024*512/t/1e9:.0f} TF/s)")
+    dh = torch.empty_like(x)
+    t = timeit(lambda: L.gemm(du, w1, dh, b_mn_major=True, aux=x, M=N, N=512, K=1024, use_tc=True)); print(f"mlp1 dgrad + residual: {t:.3f} ms ({2*N*1024*512/t/1e9:.0f} TF/s)")
 if what in ("gp", "all"):
     for (Bn, T) in [(512, 1000), (512, 500), (148, 1000), (296, 1000)]:
         x = torch.rand(Bn, T, 1, device=dev); z = torch.randn(Bn, T, device=dev)

@@ -75,6 +75,40 @@ __device__ __forceinline__ float gelu_erf_grad(float u) {
   return cdf + u * pdf;
 }
 
+// Fast erf-GELU for the bf16 tensor-core epilogues: Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7, far below bf16
+// resolution) with one MUFU.RCP and one MUFU.EX2; exp(-u^2/2) is shared between erf and the Gaussian pdf of GELU'.
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// returns erf(|u| / sqrt(2)) and exp(-u^2 / 2)
+__device__ __forceinline__ float erf_abs_as(float u, float& gauss) {
+  const float ax = fabsf(u) * 0.70710678118654752f;
+  const float t = fast_rcp(fmaf(0.3275911f, ax, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  gauss = fast_ex2(u * u * -0.72134752044448170f);        // exp(-u^2/2) = 2^(-u^2 * log2(e) / 2)
+  return fmaf(-poly * t, gauss, 1.0f);
+}
+__device__ __forceinline__ float gelu_fast(float u) {
+  float gs;
+  const float e = erf_abs_as(u, gs);
+  return 0.5f * u * (1.0f + copysignf(e, u));
+}
+__device__ __forceinline__ float gelu_grad_fast(float u) {
+  float gs;
+  const float e = erf_abs_as(u, gs);
+  return fmaf(0.39894228040143268f * u, gs, 0.5f * (1.0f + copysignf(e, u)));
+}
+
 int num_sms();
 
 }  // namespace pfn

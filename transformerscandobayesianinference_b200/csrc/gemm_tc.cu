@@ -16,6 +16,14 @@
 //   warps 2..9  : epilogue       (tcgen05.ld TMEM->regs, bias / GELU / residual / GELU'; bf16 tiles are staged in
 //                                 128B-swizzled smem and written with TMA stores, fp32/atomic outputs go direct)
 //   TMEM        : 2 accumulator stages x BLOCK_N fp32 columns (epilogue of tile i overlaps MMA of i+1)
+//
+// CTA2 = true (used whenever N > 128): clusters of two CTAs run tcgen05.mma.cta_group::2 with M = 256.  Each CTA loads its
+// own 128 rows of A and only HALF of the 256-wide B tile (the pair's tensor cores read both halves), which cuts the operand
+// traffic per MAC from 0.0234 to 0.0156 B — the 1-CTA kernel is bound by the ~12 TB/s L2->SM fabric at ~1000 TFLOP/s.
+// The leader CTA's MMA warp issues for the pair; its commits are multicast to the barriers of both CTAs; the leader's
+// `full` barriers collect the TMA bytes of both CTAs; both epilogues drain their own TMEM half and report to the leader.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "../../include/pfn_b200.h"
@@ -37,6 +45,8 @@ struct GemmTcParams {
   int k_splits;
   int kb_per_split;              // k-blocks (of 64) per split
   int tiles_m, tiles_n;
+  int l2_prefetch;               // 1 => the producer prefetches the next work item's A tile into L2
+  long long* stall;              // debug: per-CTA [4] clock sums: producer wait-empty, MMA wait-full, MMA wait-tempty, epilogue wait-tfull
   int tma_store;                 // 1 => bf16 C (and C2) leave through the smem staging buffer + TMA store
 };
 
@@ -45,25 +55,26 @@ constexpr int kBlockK = 64;
 constexpr int kNumEpiWarps = 8;
 constexpr int kNumThreads = 64 + kNumEpiWarps * 32;
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool CTA2 = false>
 struct GemmCfg {
-  static constexpr int kStagesMax = BLOCK_N == 256 ? 4 : 6;      // fp32 / atomic outputs: no staging buffer, deeper ring
-  static constexpr int kStagesStaged = BLOCK_N == 256 ? 3 : 5;   // bf16 outputs: one stage gives way to the staging buffer
-  static constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
-  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kABytes = kBlockM * kBlockK * 2;                       // 16 KB
+  static constexpr int kBBytes = (CTA2 ? BLOCK_N / 2 : BLOCK_N) * kBlockK * 2;  // a CTA of a pair holds half of the B tile
+  static constexpr int kRingBudget = 212992;                                   // 208 KB of the 227 KB for operands + staging
+  static constexpr int kStagesMax = kRingBudget / (kABytes + kBBytes) > 6 ? 6 : kRingBudget / (kABytes + kBBytes);   // no staging buffer
+  static constexpr int kStagesStaged = (kRingBudget - kBlockM * BLOCK_N * 2) / (kABytes + kBBytes);
   static constexpr int kTmemCols = 2 * BLOCK_N;
   static constexpr int kStageOutBytes = kBlockM * BLOCK_N * 2;   // bf16 output tile (two column halves, one per epilogue group)
   static constexpr int kRingBytes = kStagesMax * (kABytes + kBBytes);
   static constexpr int kStagedBytes = kStagesStaged * (kABytes + kBBytes) + kStageOutBytes;
   static constexpr int kDataBytes = kRingBytes > kStagedBytes ? kRingBytes : kStagedBytes;
-  static constexpr int kSmemBytes = kDataBytes + 256 + 1024;
+  static constexpr int kSmemBytes = kDataBytes + 512 + 1024;
 };
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+template <int BLOCK_N, bool A_MN, bool B_MN, bool CTA2>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const GemmTcParams p) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, CTA2>;
   const int STAGES = p.tma_store ? Cfg::kStagesStaged : Cfg::kStagesMax;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -78,6 +89,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = CTA2 ? tc::cluster_ctarank() : 0u;     // 0 = leader of the pair
+  const bool is_leader = cta_rank == 0;
 
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tmA);
@@ -85,86 +98,132 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (p.tma_store) { tc::tma_prefetch_desc(&tmC); if (p.C2 != nullptr) tc::tma_prefetch_desc(&tmC2); }
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < Cfg::kStagesMax; ++s) {
       tc::mbar_init(&full_bar[s], 1);
       tc::mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&tfull_bar[s], 1);
-      tc::mbar_init(&tempty_bar[s], kNumEpiWarps);
+      tc::mbar_init(&tempty_bar[s], CTA2 ? 2 * kNumEpiWarps : kNumEpiWarps);   // pair: both CTAs' epilogues report to the leader
     }
     tc::mbar_fence_init();
   }
   if (warp == 2) {
-    tc::tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tc::tmem_relinquish();
+    if constexpr (CTA2) { tc::tmem_alloc_2cta(tmem_slot, Cfg::kTmemCols); tc::tmem_relinquish_2cta(); }
+    else { tc::tmem_alloc(tmem_slot, Cfg::kTmemCols); tc::tmem_relinquish(); }
   }
   tc::tc_fence_before();
-  __syncthreads();
+  if constexpr (CTA2) tc::cluster_sync_all(); else __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_kb_total = (p.K + kBlockK - 1) / kBlockK;
-  const int tiles = p.tiles_m * p.tiles_n;
+  const int tiles = p.tiles_m * p.tiles_n;             // tiles_m counts 256-row tiles when CTA2
   const int total_work = tiles * p.k_splits;
+  const int work0 = CTA2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);   // work items are per pair
+  const int work_stride = CTA2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  constexpr int kTileM = CTA2 ? 2 * kBlockM : kBlockM;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (converged warp, elected lane issues)
     {
+      long long st_prod = 0;
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      for (int w = work0; w < total_work; w += work_stride) {
         const int split = w / tiles;
         const int tile = w - split * tiles;
-        const int m0 = (tile / p.tiles_n) * kBlockM;
+        const int m0 = (tile / p.tiles_n) * kTileM + static_cast<int>(cta_rank) * kBlockM;
         const int n0 = (tile % p.tiles_n) * BLOCK_N;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, num_kb_total);
+        // Pull the NEXT work item's A tile (the streamed operand) into L2 now: its TMA loads then see L2 latency instead
+        // of DRAM latency, which the short smem ring cannot cover.
+        if (p.l2_prefetch && w + work_stride < total_work && tc::elect_one()) {
+          const int wn = w + work_stride;
+          const int splitn = wn / tiles;
+          const int tilen = wn - splitn * tiles;
+          const int mn = (tilen / p.tiles_n) * kTileM + static_cast<int>(cta_rank) * kBlockM;
+          const int kn0 = splitn * p.kb_per_split;
+          const int kn1 = min(kn0 + p.kb_per_split, num_kb_total);
+          for (int kb = kn0; kb < kn1; ++kb) {
+            if constexpr (!A_MN) {
+              tc::tma_prefetch_2d(&tmA, kb * kBlockK, mn);
+            } else {
+              tc::tma_prefetch_2d(&tmA, mn, kb * kBlockK);
+              tc::tma_prefetch_2d(&tmA, mn + 64, kb * kBlockK);
+            }
+          }
+        }
+        __syncwarp();
         for (int kb = kb0; kb < kb1; ++kb) {
-          tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+          { const long long t0 = clock64(); tc::mbar_wait(&empty_bar[stage], phase ^ 1); st_prod += clock64() - t0; }
           uint8_t* a_dst = sA + stage * Cfg::kABytes;
           uint8_t* b_dst = sB + stage * Cfg::kBBytes;
           const int k0 = kb * kBlockK;
           if (tc::elect_one()) {
-            tc::mbar_expect_tx(&full_bar[stage], Cfg::kABytes + Cfg::kBBytes);
-            if constexpr (!A_MN) {
-              tc::tma_load_2d(a_dst, &tmA, &full_bar[stage], k0, m0);
-            } else {
+            if constexpr (!CTA2) {
+              tc::mbar_expect_tx(&full_bar[stage], Cfg::kABytes + Cfg::kBBytes);
+              if constexpr (!A_MN) {
+                tc::tma_load_2d(a_dst, &tmA, &full_bar[stage], k0, m0);
+              } else {
 #pragma unroll
-              for (int c = 0; c < kBlockM / 64; ++c)
-                tc::tma_load_2d(a_dst + c * 8192, &tmA, &full_bar[stage], m0 + c * 64, k0);
-            }
-            if constexpr (!B_MN) {
-              tc::tma_load_2d(b_dst, &tmB, &full_bar[stage], k0, n0);
-            } else {
+                for (int c = 0; c < kBlockM / 64; ++c)
+                  tc::tma_load_2d(a_dst + c * 8192, &tmA, &full_bar[stage], m0 + c * 64, k0);
+              }
+              if constexpr (!B_MN) {
+                tc::tma_load_2d(b_dst, &tmB, &full_bar[stage], k0, n0);
+              } else {
 #pragma unroll
-              for (int c = 0; c < BLOCK_N / 64; ++c)
-                tc::tma_load_2d(b_dst + c * 8192, &tmB, &full_bar[stage], n0 + c * 64, k0);
+                for (int c = 0; c < BLOCK_N / 64; ++c)
+                  tc::tma_load_2d(b_dst + c * 8192, &tmB, &full_bar[stage], n0 + c * 64, k0);
+              }
+            } else {
+              // pair: the leader arms its `full` barrier for the bytes of BOTH CTAs; each CTA loads its own A rows and its
+              // half (rank * BLOCK_N/2) of the B tile; all transaction bytes complete on the leader's barrier.
+              if (is_leader) tc::mbar_expect_tx(&full_bar[stage], 2 * (Cfg::kABytes + Cfg::kBBytes));
+              const int nh = n0 + static_cast<int>(cta_rank) * (BLOCK_N / 2);
+              if constexpr (!A_MN) {
+                tc::tma_load_2d_2cta(a_dst, &tmA, &full_bar[stage], k0, m0);
+              } else {
+#pragma unroll
+                for (int c = 0; c < kBlockM / 64; ++c)
+                  tc::tma_load_2d_2cta(a_dst + c * 8192, &tmA, &full_bar[stage], m0 + c * 64, k0);
+              }
+              if constexpr (!B_MN) {
+                tc::tma_load_2d_2cta(b_dst, &tmB, &full_bar[stage], k0, nh);
+              } else {
+#pragma unroll
+                for (int c = 0; c < BLOCK_N / 128; ++c)
+                  tc::tma_load_2d_2cta(b_dst + c * 8192, &tmB, &full_bar[stage], nh + c * 64, k0);
+              }
             }
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      if (p.stall != nullptr && lane == 0) p.stall[blockIdx.x * 4 + 0] = st_prod;
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (converged warp, elected lane issues)
-    {
-      constexpr uint32_t idesc = tc::umma_idesc_bf16(kBlockM, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    if (!CTA2 || is_leader) {
+      constexpr uint32_t idesc = tc::umma_idesc_bf16(kTileM, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      long long st_full = 0, st_tempty = 0;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+      for (int w = work0; w < total_work; w += work_stride, ++it) {
         const int split = w / tiles;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, num_kb_total);
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
-        tc::mbar_wait(&tempty_bar[as], aphase ^ 1);
+        { const long long t0 = clock64(); tc::mbar_wait(&tempty_bar[as], aphase ^ 1); st_tempty += clock64() - t0; }
         tc::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
         for (int kb = kb0; kb < kb1; ++kb) {
-          tc::mbar_wait(&full_bar[stage], phase);
+          { const long long t0 = clock64(); tc::mbar_wait(&full_bar[stage], phase); st_full += clock64() - t0; }
           tc::tc_fence_after();
           const uint32_t a_addr = tc::smem_u32(sA + stage * Cfg::kABytes);
           const uint32_t b_addr = tc::smem_u32(sB + stage * Cfg::kBBytes);
@@ -177,15 +236,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                            : tc::umma_smem_desc(a_addr + k * 32, 16, 1024);
               const uint64_t b_desc = B_MN ? tc::umma_smem_desc(b_addr + k * 2048, 8192, 1024)
                                            : tc::umma_smem_desc(b_addr + k * 32, 16, 1024);
-              tc::umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              if constexpr (CTA2) tc::umma_bf16_ss_2cta(d_tmem, a_desc, b_desc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              else tc::umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             }
-            tc::umma_commit(&empty_bar[stage]);
-            if (kb == kb1 - 1) tc::umma_commit(&tfull_bar[as]);
+            if constexpr (CTA2) {
+              tc::umma_commit_2cta(&empty_bar[stage]);                     // frees the stage in BOTH CTAs
+              if (kb == kb1 - 1) tc::umma_commit_2cta(&tfull_bar[as]);     // wakes BOTH epilogues
+            } else {
+              tc::umma_commit(&empty_bar[stage]);
+              if (kb == kb1 - 1) tc::umma_commit(&tfull_bar[as]);
+            }
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      if (p.stall != nullptr && lane == 0) { p.stall[blockIdx.x * 4 + 1] = st_full; p.stall[blockIdx.x * 4 + 2] = st_tempty; }
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
@@ -201,15 +267,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int nbar = 1 + half;                             // named barrier of this group (0 is __syncthreads)
     const bool two_pass = p.tma_store && p.act == PFN_EPI_GELU && p.C2 != nullptr;
     bool store_pending = false;
+    long long st_tfull = 0;
     int it = 0;
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+    for (int w = work0; w < total_work; w += work_stride, ++it) {
       const int split = w / tiles;
       const int tile = w - split * tiles;
-      const int m0 = (tile / p.tiles_n) * kBlockM;
+      const int m0 = (tile / p.tiles_n) * kTileM + static_cast<int>(cta_rank) * kBlockM;
       const int n0 = (tile % p.tiles_n) * BLOCK_N;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      tc::mbar_wait(&tfull_bar[as], aphase);
+      { const long long t0 = clock64(); tc::mbar_wait(&tfull_bar[as], aphase); st_tfull += clock64() - t0; }
       tc::tc_fence_after();
       const int trow = q * 32 + lane;
       const int row = m0 + trow;
@@ -270,7 +337,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
 #pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
+            for (int i = 0; i < 32; ++i) f[i] = gelu_fast(f[i]);
           }
           if (p.aux != nullptr && row_ok && !write_pre_only && (p.act == PFN_EPI_GELU_BWD || split == 0)) {
             const __nv_bfloat16* src = p.aux + static_cast<size_t>(row) * p.ld_aux + col0;
@@ -292,7 +359,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             if (p.act == PFN_EPI_GELU_BWD) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] *= gelu_erf_grad(a[i]);
+              for (int i = 0; i < 32; ++i) f[i] *= gelu_grad_fast(a[i]);
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i) f[i] += a[i];
@@ -347,7 +414,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // accumulator stage drained: hand it back to the MMA warp
           tc::tc_fence_before();
           __syncwarp();
-          if (lane == 0) tc::mbar_arrive(&tempty_bar[as]);
+          if (lane == 0) { if constexpr (CTA2) tc::mbar_arrive_leader(&tempty_bar[as]); else tc::mbar_arrive(&tempty_bar[as]); }
         }
         if (p.tma_store) {
           tc::fence_proxy_async_smem();                       // generic-proxy staging writes -> visible to the TMA
@@ -366,19 +433,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     if (p.tma_store && issuer) tc::tma_store_wait<0>();        // all bulk stores complete before the CTA exits
+    if (p.stall != nullptr && warp == 2 && lane == 0) p.stall[blockIdx.x * 4 + 3] = st_tfull;
   }
 
   tc::tc_fence_before();
-  __syncthreads();
+  if constexpr (CTA2) tc::cluster_sync_all(); else __syncthreads();   // pair: nobody frees TMEM / exits while the peer still uses it
   if (warp == 2) {
     tc::tc_fence_after();
-    tc::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if constexpr (CTA2) tc::tmem_dealloc_2cta(tmem_base, Cfg::kTmemCols); else tc::tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+template <int BLOCK_N, bool A_MN, bool B_MN, bool CTA2>
 static int launch_gemm_tc(const pfn_gemm_desc* d, cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, CTA2>;
+  constexpr int kBRows = CTA2 ? BLOCK_N / 2 : BLOCK_N;   // B rows one CTA loads per stage
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[2], strides[2];
@@ -387,7 +456,7 @@ static int launch_gemm_tc(const pfn_gemm_desc* d, cudaStream_t stream) {
     else       { dims[0] = d->M; dims[1] = d->K; box[0] = 64; box[1] = 64; }
     strides[0] = 0; strides[1] = static_cast<uint64_t>(d->lda) * 2;
     if (int rc = make_tensor_map_bf16(&tmA, d->A, 2, dims, strides, box, true)) return rc;
-    if (!B_MN) { dims[0] = d->K; dims[1] = d->N; box[0] = 64; box[1] = BLOCK_N; }
+    if (!B_MN) { dims[0] = d->K; dims[1] = d->N; box[0] = 64; box[1] = kBRows; }
     else       { dims[0] = d->N; dims[1] = d->K; box[0] = 64; box[1] = 64; }
     strides[1] = static_cast<uint64_t>(d->ldb) * 2;
     if (int rc = make_tensor_map_bf16(&tmB, d->B, 2, dims, strides, box, true)) return rc;
@@ -410,6 +479,12 @@ static int launch_gemm_tc(const pfn_gemm_desc* d, cudaStream_t stream) {
   }
   GemmTcParams p;
   p.tma_store = tma_store ? 1 : 0;
+  p.stall = g_trace_which == 10 ? g_trace_ptr : nullptr;
+  {
+    static int l2pf = -1;
+    if (l2pf < 0) { const char* e = getenv("PFN_GEMM_L2_PREFETCH"); l2pf = (e != nullptr && e[0] == '1') ? 1 : 0; }   // off by default: measured no gain
+    p.l2_prefetch = (l2pf && d->k_splits <= 1) ? 1 : 0;   // only for token-streaming GEMMs (K small, A = activations)
+  }
   p.M = d->M; p.N = d->N; p.K = d->K;
   p.bias = d->bias;
   p.aux = reinterpret_cast<const __nv_bfloat16*>(d->aux);
@@ -417,7 +492,8 @@ static int launch_gemm_tc(const pfn_gemm_desc* d, cudaStream_t stream) {
   p.C = d->C; p.ldc = d->ldc; p.c_f32 = d->c_dtype == PFN_F32;
   p.C2 = reinterpret_cast<__nv_bfloat16*>(d->C2); p.ldc2 = d->ldc2;
   p.act = d->epilogue;
-  p.tiles_m = (d->M + kBlockM - 1) / kBlockM;
+  constexpr int kTileM = CTA2 ? 2 * kBlockM : kBlockM;
+  p.tiles_m = (d->M + kTileM - 1) / kTileM;
   p.tiles_n = (d->N + BLOCK_N - 1) / BLOCK_N;
   const int num_kb = (d->K + kBlockK - 1) / kBlockK;
   int splits = d->k_splits <= 0 ? 1 : d->k_splits;
@@ -429,14 +505,31 @@ static int launch_gemm_tc(const pfn_gemm_desc* d, cudaStream_t stream) {
   p.accumulate = (d->accumulate || splits > 1) ? 1 : 0;
   PFN_CHECK_ARG(!p.accumulate || p.c_f32, "gemm_tc: accumulate / split-K requires an fp32 output");
   const int total = p.tiles_m * p.tiles_n * splits;
-  const int grid = total < num_sms() ? total : num_sms();
-  auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN>;
+  auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN, CTA2>;
   static bool attr_set = false;
   if (!attr_set) {
     PFN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  kern<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, tmC2, p);
+  if constexpr (!CTA2) {
+    const int grid = total < num_sms() ? total : num_sms();
+    kern<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, tmC2, p);
+  } else {
+    const int pairs = num_sms() / 2;
+    const int grid = 2 * (total < pairs ? total : pairs);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PFN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmC2, p));
+  }
   PFN_LAUNCH_OK();
   return 0;
 }
@@ -461,15 +554,25 @@ extern "C" int pfn_gemm_bf16_tc(const pfn_gemm_desc* d, void* stream) {
   PFN_CHECK_ARG(d->bias == nullptr || (reinterpret_cast<uintptr_t>(d->bias) & 15) == 0, "gemm_tc: bias must be 16-byte aligned");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const bool wide = d->N > 128;
+  static int use_pair = -1;
+  if (use_pair < 0) { const char* e = getenv("PFN_GEMM_2CTA"); use_pair = (e == nullptr || e[0] != '0') ? 1 : 0; }
   const int key = (wide ? 4 : 0) | (d->a_mn_major ? 2 : 0) | (d->b_mn_major ? 1 : 0);
+  if (wide && use_pair) {
+    switch (key & 3) {
+      case 0: return launch_gemm_tc<256, false, false, true>(d, s);
+      case 1: return launch_gemm_tc<256, false, true, true>(d, s);
+      case 2: return launch_gemm_tc<256, true, false, true>(d, s);
+      default: return launch_gemm_tc<256, true, true, true>(d, s);
+    }
+  }
   switch (key) {
-    case 0: return launch_gemm_tc<128, false, false>(d, s);
-    case 1: return launch_gemm_tc<128, false, true>(d, s);
-    case 2: return launch_gemm_tc<128, true, false>(d, s);
-    case 3: return launch_gemm_tc<128, true, true>(d, s);
-    case 4: return launch_gemm_tc<256, false, false>(d, s);
-    case 5: return launch_gemm_tc<256, false, true>(d, s);
-    case 6: return launch_gemm_tc<256, true, false>(d, s);
-    default: return launch_gemm_tc<256, true, true>(d, s);
+    case 0: return launch_gemm_tc<128, false, false, false>(d, s);
+    case 1: return launch_gemm_tc<128, false, true, false>(d, s);
+    case 2: return launch_gemm_tc<128, true, false, false>(d, s);
+    case 3: return launch_gemm_tc<128, true, true, false>(d, s);
+    case 4: return launch_gemm_tc<256, false, false, false>(d, s);
+    case 5: return launch_gemm_tc<256, false, true, false>(d, s);
+    case 6: return launch_gemm_tc<256, true, false, false>(d, s);
+    default: return launch_gemm_tc<256, true, true, false>(d, s);
   }
 }
