@@ -17,6 +17,17 @@ def timeit(fn, reps=5, warm=2):
 what = sys.argv[1] if len(sys.argv) > 1 else "attn"
 B, H, dh = 512, 4, 128
 E = H * dh
+if what in ("attnparts",):
+    T, sep = 1000, 500
+    qkv = (torch.randn(T * B, 3 * E, device=dev)).to(torch.bfloat16)
+    out = torch.empty(T * B, E, device=dev, dtype=torch.bfloat16); lse = torch.empty(B * H, T, device=dev)
+    dout = torch.randn(T * B, E, device=dev).to(torch.bfloat16); dqkv = torch.empty_like(qkv); delta = torch.empty_like(lse)
+    L.attention_fwd(qkv, out, lse, T, B, H, dh, sep, use_tc=True)
+    for name, sel in (("all", 0), ("dkv", 21), ("dq", 22), ("delta", 23)):
+        L.load().pfn_debug_attention_trace(None, 0, sel)
+        t = timeit(lambda: L.attention_bwd(qkv, out, lse, dout, dqkv, delta, T, B, H, dh, sep, use_tc=True))
+        print(f"attn bwd part {name}: {t:.3f} ms")
+    L.load().pfn_debug_attention_trace(None, 0, 0)
 if what in ("attn", "all"):
     for (T, sep) in [(1000, 500), (500, 500), (1000, 1000), (1000, 0), (1000, 64), (2000, 1000)]:
         qkv = (torch.randn(T * B, 3 * E, device=dev)).to(torch.bfloat16)

@@ -33,7 +33,7 @@ constexpr int AB_EW_THREADS = 256;
 constexpr int AB_EW_WARPS = 8;
 constexpr int AB_TILE_BYTES = 128 * AB_DH * 2;     // 32 KB : 128-row operand tile (2 chunks of 16 KB)
 constexpr int AB_BLK_BYTES = 64 * AB_DH * 2;       // 16 KB : 64-row operand block (2 chunks of 8 KB)
-constexpr int AB_KS = 4;                           // depth of the 64-row block ring (TMA runs 3 blocks ahead of the MMAs)
+constexpr int AB_KS = 5;                           // depth of the 64-row block ring (TMA runs 3 blocks ahead of the MMAs)
 constexpr int AB_SMEM = 2 * AB_TILE_BYTES + AB_KS * 2 * AB_BLK_BYTES + 1024 /*lse/delta*/ + 256 + 1024;   // both kernels                      // dQ kernel
 
 struct AttnBwdParams {
@@ -196,13 +196,13 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * AB_TILE_BYTES + AB_KS * 2 * AB_BLK_BYTES + 1024);
   uint64_t* qdo_full = bars + 0;
   uint64_t* qdo_empty = bars + 1;   // MMA commit after the tile's last score MMA + one arrival per row thread
-  uint64_t* kv_full = bars + 2;     // [AB_KS]
-  uint64_t* kv_empty = bars + 6;    // [AB_KS]
-  uint64_t* s_full = bars + 10;     // [2]
-  uint64_t* ds_ready = bars + 12;   // [2]
-  uint64_t* dq_done = bars + 14;
-  uint64_t* dq_empty = bars + 15;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* kv_full = bars + 2;                  // [AB_KS]
+  uint64_t* kv_empty = bars + 2 + AB_KS;         // [AB_KS]
+  uint64_t* s_full = bars + 2 + 2 * AB_KS;       // [3]
+  uint64_t* ds_ready = s_full + 3;               // [3]
+  uint64_t* dq_done = s_full + 6;
+  uint64_t* dq_empty = s_full + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -220,7 +220,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
       tc::mbar_init(&kv_full[s], 1);
       tc::mbar_init(&kv_empty[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 3; ++s) {
       tc::mbar_init(&s_full[s], 1);
       tc::mbar_init(&ds_ready[s], AB_EW_WARPS);
     }
@@ -237,7 +237,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int nblk = (p.sep + 63) / 64;
-  // TMEM columns: S[2] @0,64 | dP[2] @128,192 | dQ @256..383
+  // TMEM columns: S[3] @0,64,128 | dP[3] @192,256,320 | dQ @384..511   (three score blocks in flight)
 
   if (warp == 0) {
     {
@@ -285,10 +285,11 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
       const uint32_t q_addr = tc::smem_u32(sQ), do_addr = tc::smem_u32(sDO);
       auto issue_scores = [&](uint32_t gg) {
         const uint32_t k_addr = tc::smem_u32(sKV + (gg % AB_KS) * 2 * AB_BLK_BYTES);
+        const uint32_t sb = gg % 3;
         if (tc::elect_one()) {
-          ab_mma_ss_128x64(tmem_base + (gg & 1) * 64, q_addr, k_addr);                       // S  = Q K^T
-          ab_mma_ss_128x64(tmem_base + 128 + (gg & 1) * 64, do_addr, k_addr + AB_BLK_BYTES); // dP = dO V^T
-          tc::umma_commit(&s_full[gg & 1]);
+          ab_mma_ss_128x64(tmem_base + sb * 64, q_addr, k_addr);                        // S  = Q K^T
+          ab_mma_ss_128x64(tmem_base + 192 + sb * 64, do_addr, k_addr + AB_BLK_BYTES);  // dP = dO V^T
+          tc::umma_commit(&s_full[sb]);
         }
         __syncwarp();
       };
@@ -298,30 +299,44 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
         const int nb = ab_tile_block_plan(qt * 128, p.sep, p.T, nblk, dstart);
         tc::mbar_wait(qdo_full, tcount & 1);
         if (lane == 0) tr.log(10, tcount, 0);
-        tc::mbar_wait(&kv_full[g % AB_KS], (g / AB_KS) & 1);
-        if (lane == 0) tr.log(11, tcount, 0);
-        tc::tc_fence_after();
-        issue_scores(g);
+        // prologue: scores of the first two blocks
+        for (int pre = 0; pre < 2 && pre < nb; ++pre) {
+          const uint32_t gp = g + pre;
+          tc::mbar_wait(&kv_full[gp % AB_KS], (gp / AB_KS) & 1);
+          if (lane == 0) tr.log(11, tcount, pre);
+          tc::tc_fence_after();
+          issue_scores(gp);
+        }
+        // Barriers are probed one step early (see gemm_tc.cu: an MMA-warp stall is tensor-pipe idle time): the probe's
+        // round trip overlaps the blocking issue of the MMAs in between; the spinning wait is the fallback.
+        bool kv_ok = false;
         for (int j = 0; j < nb; ++j, ++g) {
-          if (j + 1 < nb) {
-            const uint32_t gn = g + 1;
-            tc::mbar_wait(&kv_full[gn % AB_KS], (gn / AB_KS) & 1);
-            if (lane == 0) tr.log(11, tcount, j + 1);
+          bool ds_ok = false;
+          if (j + 2 < nb) {
+            const uint32_t gn = g + 2;
+            if (!kv_ok) tc::mbar_wait(&kv_full[gn % AB_KS], (gn / AB_KS) & 1);
+            if (lane == 0) tr.log(11, tcount, j + 2);
             tc::tc_fence_after();
-            issue_scores(gn);
-          } else {
+            ds_ok = tc::mbar_try_wait(&ds_ready[g % 3], (g / 3) & 1);
+            issue_scores(gn);       // its S/dP buffer was last read by dQ-MMA of block j-1, issued before (in-order pipe)
+          } else if (j + 2 == nb) {
+            if (tc::elect_one()) tc::umma_commit(qdo_empty);   // all score MMAs of this tile are issued
+            __syncwarp();
+          }
+          if (nb == 1 && j == 0) {
             if (tc::elect_one()) tc::umma_commit(qdo_empty);
             __syncwarp();
           }
-          tc::mbar_wait(&ds_ready[g & 1], (g >> 1) & 1);
+          if (!ds_ok) tc::mbar_wait(&ds_ready[g % 3], (g / 3) & 1);
           if (lane == 0) tr.log(12, tcount, j);
           if (j == 0) tc::mbar_wait(dq_empty, (tcount & 1) ^ 1);
           tc::tc_fence_after();
+          kv_ok = (j + 3 < nb) ? tc::mbar_try_wait(&kv_full[(g + 3) % AB_KS], ((g + 3) / AB_KS) & 1) : false;
           const uint32_t k_addr = tc::smem_u32(sKV + (g % AB_KS) * 2 * AB_BLK_BYTES);
           if (tc::elect_one()) {
-            ab_mma_ts_128x128(tmem_base + 256, tmem_base + (g & 1) * 64, k_addr, j > 0);     // dQ += dS K
+            ab_mma_ts_128x128(tmem_base + 384, tmem_base + (g % 3) * 64, k_addr, j > 0);     // dQ += dS K
             tc::umma_commit(&kv_empty[g % AB_KS]);
-            tc::umma_commit(dq_done);
+            if (j + 1 == nb) tc::umma_commit(dq_done);     // one phase per tile: the parity wait below is unambiguous
           }
           __syncwarp();
           if (lane == 0) tr.log(13, tcount, j);
@@ -352,15 +367,15 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
         dls = p.delta[static_cast<size_t>(bh) * p.T + i] * p.scale;
       }
       for (int j = 0; j < nb; ++j, ++g) {
-        const uint32_t buf = g & 1;
-        tc::mbar_wait(&s_full[buf], (g >> 1) & 1);
+        const uint32_t buf = g % 3;
+        tc::mbar_wait(&s_full[buf], (g / 3) & 1);
         if (lane == 0) tr.log(20 + 100 * warp, tcount, j);
         tc::tc_fence_after();
         const bool dense = j < nblk;
         const int kmax = dense ? p.sep - j * 64 : 0;
         uint32_t s[32], dp[32], pk[16];
         tc::tmem_ld_32x32b_x32(tmem_base + lane_off + buf * 64 + half * 32, s);
-        tc::tmem_ld_32x32b_x32(tmem_base + lane_off + 128 + buf * 64 + half * 32, dp);
+        tc::tmem_ld_32x32b_x32(tmem_base + lane_off + 192 + buf * 64 + half * 32, dp);
         tc::tmem_ld_wait();
         if (dense && kmax >= 64) {
 #pragma unroll
@@ -425,9 +440,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
         if (lane == 0) tr.log(21 + 100 * warp, tcount, j);
       }
       tc::mbar_arrive_warp(qdo_empty);                        // this thread no longer reads the Q / dO tiles
-      // phase-parity safety (see attention_tc.cu): observe dq_done phases g-2 then g-1, in order
-      if (nb >= 2) tc::mbar_wait(dq_done, (g - 2) & 1);
-      tc::mbar_wait(dq_done, (g - 1) & 1);
+      tc::mbar_wait(dq_done, tcount & 1);                     // committed once per tile, after its last dQ MMA
       if (lane == 0) tr.log(22 + 100 * warp, tcount, 0);
       tc::tc_fence_after();
       const size_t tok = p.batch_major ? static_cast<size_t>(b) * p.T + (valid ? i : 0) : static_cast<size_t>(valid ? i : 0) * p.B + b;
@@ -437,7 +450,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
         const int c = half * 2 + cc;                      // the pair splits the four 32-column chunks
         uint32_t raw[32];
         float acc[32];
-        tc::tmem_ld_32x32b_x32(tmem_base + lane_off + 256 + c * 32, raw);
+        tc::tmem_ld_32x32b_x32(tmem_base + lane_off + 384 + c * 32, raw);
         tc::tmem_ld_wait();
 #pragma unroll
         for (int e = 0; e < 32; ++e) acc[e] = __uint_as_float(raw[e]);
@@ -472,13 +485,15 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * AB_TILE_BYTES + AB_KS * 2 * AB_BLK_BYTES + 1024);
   uint64_t* kv_full = bars + 0;
   uint64_t* kv_empty = bars + 1;
-  uint64_t* qd_full = bars + 2;     // [AB_KS]
-  uint64_t* qd_empty = bars + 6;    // [AB_KS]
-  uint64_t* st_full = bars + 10;    // [2]
-  uint64_t* pds_ready = bars + 12;  // [2]
-  uint64_t* acc_done = bars + 14;
-  uint64_t* acc_empty = bars + 15;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* qd_full = bars + 2;                  // [AB_KS]
+  uint64_t* qd_empty = bars + 2 + AB_KS;         // [AB_KS]
+  uint64_t* st_full = bars + 2 + 2 * AB_KS;      // S^T / dP^T of a block are in TMEM (one phase per block)
+  uint64_t* s_consumed = st_full + 1;            // every row thread has read them into registers (one phase per block)
+  uint64_t* pds_ready = st_full + 2;             // [2] P^T / dS^T written (bf16, TMEM)
+  uint64_t* pd_free = st_full + 4;               // [2] the dV / dK MMAs that read that P^T / dS^T buffer are complete
+  uint64_t* acc_done = st_full + 6;
+  uint64_t* acc_empty = st_full + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(st_full + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -496,9 +511,11 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
       tc::mbar_init(&qd_full[s], 1);
       tc::mbar_init(&qd_empty[s], 1);
     }
+    tc::mbar_init(st_full, 1);
+    tc::mbar_init(s_consumed, AB_EW_WARPS);
     for (int s = 0; s < 2; ++s) {
-      tc::mbar_init(&st_full[s], 1);
       tc::mbar_init(&pds_ready[s], AB_EW_WARPS);
+      tc::mbar_init(&pd_free[s], 1);
     }
     tc::mbar_init(acc_done, 1);
     tc::mbar_init(acc_empty, AB_EW_WARPS);
@@ -513,7 +530,10 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int nq = (p.T + 63) / 64;
-  // TMEM columns: S^T[2] @0,64 | dP^T[2] @128,192 | dV @256 | dK @384
+  // TMEM columns: S^T @0 | dP^T @64 | P^T[2] @128,192 (32 cols, bf16) | dS^T[2] @160,224 | dV @256 | dK @384.
+  // The fp32 score buffer is single: it is free again as soon as the row threads have pulled it into registers
+  // (s_consumed), so the next block's score MMAs run under this block's exp/convert work, while the bf16 P^T / dS^T
+  // operands of the accumulate MMAs are double-buffered on their own columns.
 
   if (warp == 0) {
     {
@@ -552,42 +572,47 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
   } else if (warp == 1) {
     {
       const uint32_t k_addr = tc::smem_u32(sK), v_addr = tc::smem_u32(sV);
+      tc::KernelTrace tr = tc::trace_make(p.trace, p.trace_cap, 1);
       uint32_t g = 0, tcount = 0;
       auto issue_scores = [&](uint32_t gg) {
         const uint32_t q_addr = tc::smem_u32(sQD + (gg % AB_KS) * 2 * AB_BLK_BYTES);
+        tc::mbar_wait(&qd_full[gg % AB_KS], (gg / AB_KS) & 1);
+        if (gg > 0) tc::mbar_wait(s_consumed, (gg - 1) & 1);      // the previous block's scores are in registers
+        tc::tc_fence_after();
+        if (lane == 0) tr.log(11, tcount, gg);
         if (tc::elect_one()) {
-          ab_mma_ss_128x64(tmem_base + (gg & 1) * 64, k_addr, q_addr);                        // S^T  = K Q^T
-          ab_mma_ss_128x64(tmem_base + 128 + (gg & 1) * 64, v_addr, q_addr + AB_BLK_BYTES);   // dP^T = V dO^T
-          tc::umma_commit(&st_full[gg & 1]);
+          ab_mma_ss_128x64(tmem_base, k_addr, q_addr);                             // S^T  = K Q^T
+          ab_mma_ss_128x64(tmem_base + 64, v_addr, q_addr + AB_BLK_BYTES);         // dP^T = V dO^T
+          tc::umma_commit(st_full);
         }
         __syncwarp();
+        if (lane == 0) tr.log(14, tcount, gg);
       };
       for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
         tc::mbar_wait(kv_full, tcount & 1);
-        tc::mbar_wait(&qd_full[g % AB_KS], (g / AB_KS) & 1);
-        tc::tc_fence_after();
         issue_scores(g);
         for (int i = 0; i < nq; ++i, ++g) {
           if (i + 1 < nq) {
-            const uint32_t gn = g + 1;
-            tc::mbar_wait(&qd_full[gn % AB_KS], (gn / AB_KS) & 1);
-            tc::tc_fence_after();
-            issue_scores(gn);
+            issue_scores(g + 1);
           } else {
             if (tc::elect_one()) tc::umma_commit(kv_empty);
             __syncwarp();
           }
-          tc::mbar_wait(&pds_ready[g & 1], (g >> 1) & 1);
+          const uint32_t buf = g & 1;
+          tc::mbar_wait(&pds_ready[buf], (g >> 1) & 1);
+          if (lane == 0) tr.log(12, tcount, i);
           if (i == 0) tc::mbar_wait(acc_empty, (tcount & 1) ^ 1);
           tc::tc_fence_after();
           const uint32_t q_addr = tc::smem_u32(sQD + (g % AB_KS) * 2 * AB_BLK_BYTES);
           if (tc::elect_one()) {
-            ab_mma_ts_128x128(tmem_base + 256, tmem_base + (g & 1) * 64, q_addr + AB_BLK_BYTES, i > 0);   // dV += P^T dO
-            ab_mma_ts_128x128(tmem_base + 384, tmem_base + 128 + (g & 1) * 64, q_addr, i > 0);            // dK += dS^T Q
+            ab_mma_ts_128x128(tmem_base + 256, tmem_base + 128 + buf * 64, q_addr + AB_BLK_BYTES, i > 0);   // dV += P^T dO
+            ab_mma_ts_128x128(tmem_base + 384, tmem_base + 160 + buf * 64, q_addr, i > 0);                  // dK += dS^T Q
             tc::umma_commit(&qd_empty[g % AB_KS]);
-            tc::umma_commit(acc_done);
+            tc::umma_commit(&pd_free[buf]);
+            if (i + 1 == nq) tc::umma_commit(acc_done);    // one phase per tile
           }
           __syncwarp();
+          if (lane == 0) tr.log(13, tcount, i);
         }
       }
     }
@@ -597,8 +622,27 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
     const int row = quarter * 32 + lane;           // key within the tile
     const int st_tid = threadIdx.x - 64;           // 0..255
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    uint32_t g = 0;
-    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+    tc::KernelTrace tr = tc::trace_make(p.trace, p.trace_cap, warp);
+    uint32_t g = 0, tcount = 0;
+    // Row statistics (lse * log2e, delta * scale) of a 64-row block, one value per thread 0..127.  They are fetched one
+    // block AHEAD into a register and parked in the other smem buffer after this block's bar.sync, so the global-load
+    // latency is off the per-block critical path.
+    // load_stat returns the RAW global value (no arithmetic on it, so nothing waits for the load where it is issued);
+    // finish_stat applies the scaling / row masking when the value is parked in shared memory a block later.
+    auto load_stat = [&](int ww, int ii) -> float {
+      if (st_tid >= 128 || ww >= p.total_work) return 0.f;
+      const int bh2 = ww / p.n_tiles;
+      const int r = min(ii * 64 + (st_tid & 63), p.T - 1);
+      const float* src = st_tid < 64 ? p.lse : p.delta;
+      return __ldg(src + static_cast<size_t>(bh2) * p.T + r);
+    };
+    auto finish_stat = [&](float raw, int ii) -> float {
+      const bool ok = ii * 64 + (st_tid & 63) < p.T;
+      if (st_tid < 64) return ok ? raw * 1.4426950408889634f : INFINITY;
+      return ok ? raw * p.scale : 0.f;
+    };
+    if (st_tid < 128 && static_cast<int>(blockIdx.x) < p.total_work) sStat[st_tid] = finish_stat(load_stat(blockIdx.x, 0), 0);
+    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
       const int bh = w / p.n_tiles;
       const int kt = w - bh * p.n_tiles;
       const int b = bh / p.H, h = bh - b * p.H;
@@ -607,21 +651,19 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
       for (int i = 0; i < nq; ++i, ++g) {
         const uint32_t buf = g & 1;
         float* stat = sStat + buf * 128;
-        if (st_tid < 128) {
-          const int r = i * 64 + (st_tid & 63);
-          float v;
-          if (st_tid < 64) v = r < p.T ? p.lse[static_cast<size_t>(bh) * p.T + r] * 1.4426950408889634f : INFINITY;
-          else v = r < p.T ? p.delta[static_cast<size_t>(bh) * p.T + r] * p.scale : 0.f;       // delta * scale
-          stat[st_tid] = v;
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        tc::mbar_wait(&st_full[buf], (g >> 1) & 1);
+        const float stat_next = (i + 1 < nq) ? load_stat(w, i + 1) : load_stat(w + gridDim.x, 0);
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // stat[buf] visible; everyone is done reading stat[buf ^ 1]
+        if (lane == 0) tr.log(24 + 100 * warp, tcount, i);
+        tc::mbar_wait(st_full, g & 1);
+        if (lane == 0) tr.log(20 + 100 * warp, tcount, i);
         tc::tc_fence_after();
         {
           uint32_t s[32], dp[32], pkp[16], pkd[16];
-          tc::tmem_ld_32x32b_x32(tmem_base + lane_off + buf * 64 + half * 32, s);
-          tc::tmem_ld_32x32b_x32(tmem_base + lane_off + 128 + buf * 64 + half * 32, dp);
+          tc::tmem_ld_32x32b_x32(tmem_base + lane_off + half * 32, s);
+          tc::tmem_ld_32x32b_x32(tmem_base + lane_off + 64 + half * 32, dp);
           tc::tmem_ld_wait();
+          tc::tc_fence_before();
+          tc::mbar_arrive_warp(s_consumed);          // the score buffer may be overwritten by the next block's MMAs
           if (key_ok) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
@@ -643,16 +685,18 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
 #pragma unroll
             for (int c = 0; c < 16; ++c) { pkp[c] = 0u; pkd[c] = 0u; }
           }
-          tc::tmem_st_32x32b_x16(tmem_base + lane_off + buf * 64 + half * 16, pkp);
-          tc::tmem_st_32x32b_x16(tmem_base + lane_off + 128 + buf * 64 + half * 16, pkd);
+          tc::mbar_wait(&pd_free[buf], ((g >> 1) & 1) ^ 1);      // accumulate MMAs of block g-2 no longer read this buffer
+          tc::tc_fence_after();
+          tc::tmem_st_32x32b_x16(tmem_base + lane_off + 128 + buf * 64 + half * 16, pkp);
+          tc::tmem_st_32x32b_x16(tmem_base + lane_off + 160 + buf * 64 + half * 16, pkd);
         }
         tc::tmem_st_wait();
         tc::tc_fence_before();
         tc::mbar_arrive_warp(&pds_ready[buf]);
+        if (st_tid < 128) sStat[(buf ^ 1) * 128 + st_tid] = finish_stat(stat_next, i + 1 < nq ? i + 1 : 0);   // parked for the next block
+        if (lane == 0) tr.log(21 + 100 * warp, tcount, i);
       }
-      // phase-parity safety (see attention_tc.cu): observe acc_done phases g-2 then g-1, in order
-      if (nq >= 2) tc::mbar_wait(acc_done, (g - 2) & 1);
-      tc::mbar_wait(acc_done, (g - 1) & 1);
+      tc::mbar_wait(acc_done, tcount & 1);                    // committed once per tile, after its last dV/dK MMA
       tc::tc_fence_after();
       const bool store_ok = j < p.sep && j < p.T;
       const size_t krow = p.batch_major ? static_cast<size_t>(b) * p.T + (store_ok ? j : 0) : static_cast<size_t>(store_ok ? j : 0) * p.B + b;
@@ -725,14 +769,16 @@ extern "C" int pfn_attention_bwd_tc(const pfn_attn_desc* d, void* stream) {
     attr_set = true;
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  {
+  // debug only (tools/time_kernels.py): pfn_debug_attention_trace(NULL, 0, 21|22|23) runs just dK/dV | dQ | delta
+  const int only = (g_trace_ptr == nullptr && g_trace_which >= 21 && g_trace_which <= 23) ? g_trace_which : 0;
+  if (only == 0 || only == 23) {
     const long long rows = static_cast<long long>(d->T) * d->B;
     long long grid = (rows + 7) / 8;
     if (grid > 8LL * num_sms()) grid = 8LL * num_sms();
     attn_bwd_delta_kernel<<<static_cast<int>(grid), 256, 0, s>>>(p.out, p.ld_out, p.dout, p.ld_dout, p.delta, d->T, d->B, d->H, d->batch_major);
     PFN_LAUNCH_OK();
   }
-  {
+  if (only == 0 || only == 22) {
     p.n_tiles = (d->T + 127) / 128;
     p.total_work = p.n_tiles * d->B * d->H;
     int grid = num_sms() < p.total_work ? num_sms() : p.total_work;
@@ -741,11 +787,13 @@ extern "C" int pfn_attention_bwd_tc(const pfn_attn_desc* d, void* stream) {
     p.trace = nullptr;
     PFN_LAUNCH_OK();
   }
-  if (d->sep > 0) {
+  if (d->sep > 0 && (only == 0 || only == 21)) {
     p.n_tiles = (d->sep + 127) / 128;
     p.total_work = p.n_tiles * d->B * d->H;
     int grid = num_sms() < p.total_work ? num_sms() : p.total_work;
+    p.trace = g_trace_which == 2 ? g_trace_ptr : nullptr;
     attn_bwd_dkv_tc_kernel<<<grid, AB_THREADS, AB_SMEM, s>>>(tmQKV128, tmQKV64, tmDO64, p);
+    p.trace = nullptr;
     PFN_LAUNCH_OK();
   }
   return 0;

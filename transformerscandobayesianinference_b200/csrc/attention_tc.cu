@@ -111,7 +111,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* p_ready = bars + 8;        // [2]
   uint64_t* pv_done = bars + 10;
   uint64_t* o_empty = bars + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* o_done = bars + 12;        // one phase per tile: committed after the tile's last P V
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -132,6 +133,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     tc::mbar_init(pv_done, 1);
     tc::mbar_init(o_empty, 4);
+    tc::mbar_init(o_done, 1);
     tc::mbar_fence_init();
   }
   if (warp == 2) {
@@ -219,17 +221,19 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc::tc_fence_after();
         issue_qk(g);
         for (int j = 0; j < nb; ++j, ++g) {
+          bool p_ok = false;        // p_ready probed before the (blocking) Q K^T issue; see gemm_tc.cu on early probes
           if (j + 1 < nb) {
             const uint32_t gn = g + 1;
             tc::mbar_wait(&kv_full[gn & 1], (gn >> 1) & 1);
             if (lane == 0) tr.log(11, tcount, j + 1);
             tc::tc_fence_after();
+            p_ok = tc::mbar_try_wait(&p_ready[g & 1], (g >> 1) & 1);
             issue_qk(gn);
           } else {
             if (tc::elect_one()) tc::umma_commit(q_empty);   // every QK^T of this tile has been issued
             __syncwarp();
           }
-          tc::mbar_wait(&p_ready[g & 1], (g >> 1) & 1);
+          if (!p_ok) tc::mbar_wait(&p_ready[g & 1], (g >> 1) & 1);
           if (lane == 0) tr.log(12, tcount, j);  // P ready seen by MMA warp
           if (j == 0) tc::mbar_wait(o_empty, (tcount & 1) ^ 1);
           tc::tc_fence_after();
@@ -245,6 +249,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             }
             tc::umma_commit(&kv_empty[st]);
             tc::umma_commit(pv_done);
+            if (j + 1 == nb) tc::umma_commit(o_done);
           }
           __syncwarp();
           if (lane == 0) tr.log(13, tcount, j);  // PV issued
@@ -257,8 +262,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int row = quarter * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     tc::KernelTrace tr = tc::trace_make(p.trace, p.trace_cap, 2);
-    uint32_t g = 0;
-    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+    uint32_t g = 0, tcount = 0;
+    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
       const int bh = w / p.n_qtiles;
       const int qt = w - bh * p.n_qtiles;
       const int b = bh / p.H, h = bh - b * p.H;
@@ -373,10 +378,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (threadIdx.x == 64) tr.log(21, w, j);   // P published
       }
       // ---- epilogue: O / l, lse   (every valid row has seen at least one key: a train key or itself)
-      // Phase-parity safety: having seen the last S, this thread knows P V of block nb-3 is complete, so pv_done is at
-      // most two phases behind; observe phase g-2 (if any in this tile) and then g-1, in order.
-      if (nb >= 2) tc::mbar_wait(pv_done, (g - 2) & 1);
-      tc::mbar_wait(pv_done, (g - 1) & 1);
+      // o_done advances once per tile (and tile t+1's commit needs this thread's o_empty arrival), so its parity is unambiguous
+      tc::mbar_wait(o_done, tcount & 1);
       if (threadIdx.x == 64) tr.log(22, w, 0);     // epilogue start
       tc::tc_fence_after();
       const float inv_l = 1.0f / l;

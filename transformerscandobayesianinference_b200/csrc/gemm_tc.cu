@@ -157,7 +157,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
         for (int kb = kb0; kb < kb1; ++kb) {
-          { const long long t0 = clock64(); tc::mbar_wait(&empty_bar[stage], phase ^ 1); st_prod += clock64() - t0; }
+          if (p.stall != nullptr) { const long long t0 = clock64(); tc::mbar_wait(&empty_bar[stage], phase ^ 1); st_prod += clock64() - t0; }
+          else tc::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* a_dst = sA + stage * Cfg::kABytes;
           uint8_t* b_dst = sB + stage * Cfg::kBBytes;
           const int k0 = kb * kBlockK;
@@ -209,22 +210,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------------------------ MMA issuer (converged warp, elected lane issues)
     if (!CTA2 || is_leader) {
       constexpr uint32_t idesc = tc::umma_idesc_bf16(kTileM, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      // The tcgen05 issue queue is shallow (tools/ubench/mma_queue.cu: an instruction-latency gap in this warp is tensor-pipe
+      // idle time, and a ready mbarrier probe costs ~125 clocks), so every barrier this warp needs is probed one step EARLY:
+      // the probe's shared-memory round trip overlaps the (blocking) issue of the current MMAs, and the slow spinning wait is
+      // only taken when the early probe said "not yet".
+      const bool timing = p.stall != nullptr;
       long long st_full = 0, st_tempty = 0;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      bool full_ready = false;      // early probe result for full_bar[stage] / phase
+      bool tempty_ready = false;    // early probe result for the next tile's accumulator stage
       for (int w = work0; w < total_work; w += work_stride, ++it) {
         const int split = w / tiles;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, num_kb_total);
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
-        { const long long t0 = clock64(); tc::mbar_wait(&tempty_bar[as], aphase ^ 1); st_tempty += clock64() - t0; }
+        if (!tempty_ready) {
+          const long long t0 = timing ? clock64() : 0;
+          tc::mbar_wait(&tempty_bar[as], aphase ^ 1);
+          if (timing) st_tempty += clock64() - t0;
+        }
+        tempty_ready = false;
         tc::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
         for (int kb = kb0; kb < kb1; ++kb) {
-          { const long long t0 = clock64(); tc::mbar_wait(&full_bar[stage], phase); st_full += clock64() - t0; }
+          if (!full_ready) {
+            const long long t0 = timing ? clock64() : 0;
+            tc::mbar_wait(&full_bar[stage], phase);
+            if (timing) st_full += clock64() - t0;
+          }
           tc::tc_fence_after();
+          {
+            // early probes, consumed after the MMAs below have been issued
+            const int ns = (stage + 1 == STAGES) ? 0 : stage + 1;
+            const uint32_t nph = (stage + 1 == STAGES) ? (phase ^ 1) : phase;
+            full_ready = tc::mbar_try_wait(&full_bar[ns], nph);
+            if (kb == kb1 - 1) tempty_ready = tc::mbar_try_wait(&tempty_bar[as ^ 1], (((it + 1) >> 1) & 1) ^ 1);
+          }
           const uint32_t a_addr = tc::smem_u32(sA + stage * Cfg::kABytes);
           const uint32_t b_addr = tc::smem_u32(sB + stage * Cfg::kBBytes);
           if (tc::elect_one()) {
@@ -276,7 +300,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n0 = (tile % p.tiles_n) * BLOCK_N;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      { const long long t0 = clock64(); tc::mbar_wait(&tfull_bar[as], aphase); st_tfull += clock64() - t0; }
+      if (p.stall != nullptr) { const long long t0 = clock64(); tc::mbar_wait(&tfull_bar[as], aphase); st_tfull += clock64() - t0; }
+      else tc::mbar_wait(&tfull_bar[as], aphase);
       tc::tc_fence_after();
       const int trow = q * 32 + lane;
       const int row = m0 + trow;
