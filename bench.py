@@ -12,6 +12,7 @@ Metric (BASELINE.json): prior-sampled sequences / second.  Workload = configs[1]
 1 feature, emsize 512, 6 layers, nhid 1024, 4 heads, 100 bars, single_eval_pos 500, bf16, batch 512 per GPU.
 """
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -148,7 +149,8 @@ def run_engine(args):
     parallel.broadcast_parameters(model)
     torch.manual_seed(1234 + rank)
     ys = priors.fast_gp.get_batch(64, T, F, device=str(dev), hyperparameters=cfg["hps"])[1]
-    borders = bar_distribution.get_bucket_limits(n_bars, ys=ys.float().cpu())
+    with contextlib.redirect_stdout(sys.stderr):      # the reference-style helper prints; stdout carries the JSON line only
+        borders = bar_distribution.get_bucket_limits(n_bars, ys=ys.float().cpu())
     crit = bar_distribution.FullSupportBarDistribution(borders).to(dev)
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
     params = [p for p in model.parameters()]

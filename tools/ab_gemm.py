@@ -1,0 +1,36 @@
+"""A/B timing of GEMM epilogue variants on ONE GPU in ONE session: each variant library (tools/build_variants.sh) runs in
+its own subprocess (PFN_B200_LIB), interleaved twice so clock/power drift shows up as the spread between rounds."""
+import os, subprocess, sys
+HERE = os.path.dirname(os.path.abspath(__file__))
+CHILD = r'''
+import sys, os
+sys.path.insert(0, os.path.dirname(HERE))
+import torch
+from transformerscandobayesianinference_b200 import _lib as L
+dev = torch.device("cuda:0"); N = 512000
+def t(fn, reps=20):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+out = []
+for (Nn, K, bmn, name) in [(1024, 512, 0, "plain"), (1024, 512, 0, "gelu+c2"), (1024, 512, 1, "gelu'"), (512, 512, 0, "+aux"), (512, 1024, 0, "+aux K1024")]:
+    A = torch.randn(N, K, device=dev).to(torch.bfloat16)
+    Bm = torch.randn((K, Nn) if bmn else (Nn, K), device=dev).to(torch.bfloat16)
+    C = torch.zeros(N, Nn, device=dev, dtype=torch.bfloat16)
+    kw = {}
+    if name == "gelu+c2": kw = dict(bias=torch.randn(Nn, device=dev), C2=torch.empty_like(C), epilogue=1)
+    elif name == "gelu'": kw = dict(aux=torch.randn(N, Nn, device=dev).to(torch.bfloat16), epilogue=2)
+    elif name.startswith("+aux"): kw = dict(bias=torch.randn(Nn, device=dev), aux=torch.randn(N, Nn, device=dev).to(torch.bfloat16))
+    out.append(f"{name} {t(lambda: L.gemm(A, Bm, C, b_mn_major=bool(bmn), M=N, N=Nn, K=K, use_tc=True, **kw)):.3f}")
+print(" | ".join(out))
+'''.replace("HERE", repr(HERE))
+variants = sys.argv[1:] or ["tanh1", "logi1", "tanh2", "logi1nopf"]
+for rnd in range(2):
+    for v in variants:
+        env = dict(os.environ, PFN_B200_LIB=os.path.join(HERE, "ubench", "_bin", f"libpfn_{v}.so"))
+        r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True, timeout=300)
+        print(f"[{rnd}] {v:10s}: {r.stdout.strip() or r.stderr.strip()[-300:]}", flush=True)

@@ -9,7 +9,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpfn_b200.so")
+# PFN_B200_LIB points at another build of the same library (A/B measurements of kernel variants); default: the in-tree build
+LIB_PATH = os.environ.get("PFN_B200_LIB") or os.path.join(_HERE, "libpfn_b200.so")
 
 F32, BF16 = 0, 1
 EPI_NONE, EPI_GELU, EPI_GELU_BWD = 0, 1, 2

@@ -46,7 +46,7 @@ struct GemmTcParams {
   int kb_per_split;              // k-blocks (of 64) per split
   int tiles_m, tiles_n;
   int l2_prefetch;               // 1 => the producer prefetches the next work item's A tile into L2
-  long long* stall;              // debug: per-CTA [4] clock sums: producer wait-empty, MMA wait-full, MMA wait-tempty, epilogue wait-tfull
+  long long* stall;              // debug: per-CTA [8] clock sums: producer wait-empty, MMA wait-full, MMA wait-tempty, epilogue wait-tfull, epilogue wait-staging (store read + group barrier), epilogue column loop
   int tma_store;                 // 1 => bf16 C (and C2) leave through the smem staging buffer + TMA store
 };
 
@@ -204,7 +204,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
-      if (p.stall != nullptr && lane == 0) p.stall[blockIdx.x * 4 + 0] = st_prod;
+      if (p.stall != nullptr && lane == 0) p.stall[blockIdx.x * 8 + 0] = st_prod;
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (converged warp, elected lane issues)
@@ -275,7 +275,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
-      if (p.stall != nullptr && lane == 0) { p.stall[blockIdx.x * 4 + 1] = st_full; p.stall[blockIdx.x * 4 + 2] = st_tempty; }
+      if (p.stall != nullptr && lane == 0) { p.stall[blockIdx.x * 8 + 1] = st_full; p.stall[blockIdx.x * 8 + 2] = st_tempty; }
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
@@ -289,9 +289,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* stg = sOut + half * (Cfg::kStageOutBytes / 2);
     const bool issuer = (ew & 3) == 0 && lane == 0;       // the one thread per group that owns the bulk-store groups
     const int nbar = 1 + half;                             // named barrier of this group (0 is __syncthreads)
-    const bool two_pass = p.tma_store && p.act == PFN_EPI_GELU && p.C2 != nullptr;
+    // GELU with a second (pre-activation) output: BLOCK_N = 256 tiles run ONE pass over the accumulator in two rounds of 64
+    // columns, staging u in chunk slot 0 and GELU(u) in slot 1 (two bulk stores per round); the narrow tile keeps two passes.
+    const bool gelu_c2 = p.tma_store && p.act == PFN_EPI_GELU && p.C2 != nullptr;
+    const bool dual = gelu_c2 && OUT_CHUNKS >= 2;
+    const bool two_pass = gelu_c2 && !dual;
+    const bool use_aux = p.aux != nullptr;
     bool store_pending = false;
-    long long st_tfull = 0;
+    long long st_tfull = 0, st_stage = 0, st_cols = 0;
     int it = 0;
     for (int w = work0; w < total_work; w += work_stride, ++it) {
       const int split = w / tiles;
@@ -300,36 +305,74 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n0 = (tile % p.tiles_n) * BLOCK_N;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      if (p.stall != nullptr) { const long long t0 = clock64(); tc::mbar_wait(&tfull_bar[as], aphase); st_tfull += clock64() - t0; }
-      else tc::mbar_wait(&tfull_bar[as], aphase);
-      tc::tc_fence_after();
       const int trow = q * 32 + lane;
       const int row = m0 + trow;
       const bool row_ok = row < p.M;
       const bool add_bias = p.bias != nullptr && split == 0;
-      const int npass = two_pass ? 2 : 1;
+      const bool aux_now = use_aux && row_ok && (p.act == PFN_EPI_GELU_BWD || split == 0);
+      const int gcol0 = n0 + half * COLS_PER_GROUP;          // first column of this group
+      // Software pipeline: the aux (residual / pre-activation) row segment and the TMEM chunk of step c+1 are requested
+      // before step c is computed; the very first aux request goes out before the accumulator is even complete.
+      uint4 aq[4];                // aux of the next chunk (two chunks ahead measured slower: tools/ab_gemm.py)
+      auto aux_request = [&](int cc, uint4 (&dst)[4]) {
+        const __nv_bfloat16* src = p.aux + static_cast<size_t>(row) * p.ld_aux + gcol0 + cc;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dst[i] = __ldg(reinterpret_cast<const uint4*>(src) + i);
+      };
+      auto aux_fast = [&](int cc) { return aux_now && gcol0 + cc + 32 <= p.N; };
+      if (aux_fast(0)) aux_request(0, aq);
+      if (use_aux && w + work_stride < total_work) {
+        // pull the NEXT tile's aux row segment (COLS_PER_GROUP bf16 = 128 / 256 B) towards L2 while this tile is processed
+        const int w2 = w + work_stride;
+        const int tile2 = w2 - (w2 / tiles) * tiles;
+        const int row2 = (tile2 / p.tiles_n) * kTileM + static_cast<int>(cta_rank) * kBlockM + trow;
+        const int col2 = (tile2 % p.tiles_n) * BLOCK_N + half * COLS_PER_GROUP;
+        if (row2 < p.M && col2 < p.N) {
+          const char* pa = reinterpret_cast<const char*>(p.aux + static_cast<size_t>(row2) * p.ld_aux + col2);
+#pragma unroll
+          for (int o = 0; o < COLS_PER_GROUP * 2; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + o));
+        }
+      }
+      if (p.stall != nullptr) { const long long t0 = clock64(); tc::mbar_wait(&tfull_bar[as], aphase); st_tfull += clock64() - t0; }
+      else tc::mbar_wait(&tfull_bar[as], aphase);
+      tc::tc_fence_after();
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BLOCK_N + half * COLS_PER_GROUP);
+      const int npass = (dual || two_pass) ? 2 : 1;
 #pragma unroll 1
       for (int pass = 0; pass < npass; ++pass) {
-        // pass 0 of a two-pass tile writes the pre-activation (C2), the last pass writes C
+        // two_pass: pass 0 writes the pre-activation (C2), pass 1 writes C.  dual: pass = 64-column round.
         const bool write_pre_only = two_pass && pass == 0;
+        const int cc_begin = dual ? pass * 64 : 0;
+        const int cc_end = dual ? cc_begin + 64 : COLS_PER_GROUP;
         if (p.tma_store && store_pending) {
           // the previous bulk store must have finished READING the staging buffer before it is overwritten
+          const long long t0 = p.stall != nullptr ? clock64() : 0;
           if (issuer) tc::tma_store_wait_read<0>();
           asm volatile("bar.sync %0, 128;" ::"r"(nbar) : "memory");
+          if (p.stall != nullptr) st_stage += clock64() - t0;
           store_pending = false;
         }
+        const long long tc0 = p.stall != nullptr ? clock64() : 0;
+        uint32_t v[32];
+        if (gcol0 + cc_begin < p.N) tc::tmem_ld_32x32b_x32(tbase + cc_begin, v);
+        if (pass > 0) {           // (aux never accompanies a second pass today; kept correct)
+          if (aux_fast(cc_begin)) aux_request(cc_begin, aq);
+        }
 #pragma unroll 1
-        for (int cc = 0; cc < COLS_PER_GROUP; cc += 32) {
-          const int col0 = n0 + half * COLS_PER_GROUP + cc;
+        for (int cc = cc_begin; cc < cc_end; cc += 32) {
+          const int col0 = gcol0 + cc;
           if (col0 >= p.N) break;  // warp-uniform
-          uint32_t v[32];
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                                 static_cast<uint32_t>(as * BLOCK_N + half * COLS_PER_GROUP + cc);
-          tc::tmem_ld_32x32b_x32(taddr, v);
           tc::tmem_ld_wait();
           float f[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          const bool have_aux = aux_fast(cc);
+          uint4 ac[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) ac[i] = aq[i];
+          if (cc + 32 < cc_end && col0 + 32 < p.N)
+            tc::tmem_ld_32x32b_x32(tbase + cc + 32, v);               // in flight while this chunk is computed
+          if (cc + 32 < cc_end && aux_fast(cc + 32)) aux_request(cc + 32, aq);
           const bool full_chunk = (col0 + 32 <= p.N);
           if (add_bias) {
             if (full_chunk) {
@@ -345,7 +388,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           if (p.act == PFN_EPI_GELU && !write_pre_only) {
-            if (p.C2 != nullptr && row_ok && !p.tma_store) {
+            if (dual) {
+              // pre-activation goes to chunk slot 0 of the staging buffer (same swizzle as the main output below)
+              uint8_t* rowp = stg + trow * 128;
+              const int u0 = (cc & 63) >> 3;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint4 pk;
+                pk.x = tc::pack_bf16x2(f[8 * i], f[8 * i + 1]); pk.y = tc::pack_bf16x2(f[8 * i + 2], f[8 * i + 3]);
+                pk.z = tc::pack_bf16x2(f[8 * i + 4], f[8 * i + 5]); pk.w = tc::pack_bf16x2(f[8 * i + 6], f[8 * i + 7]);
+                *reinterpret_cast<uint4*>(rowp + (((u0 + i) ^ (trow & 7)) << 4)) = pk;
+              }
+            } else if (p.C2 != nullptr && row_ok && !p.tma_store) {
               __nv_bfloat16* dst = p.C2 + static_cast<size_t>(row) * p.ldc2 + col0;
               if (full_chunk) {
 #pragma unroll
@@ -364,21 +418,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = gelu_fast(f[i]);
           }
-          if (p.aux != nullptr && row_ok && !write_pre_only && (p.act == PFN_EPI_GELU_BWD || split == 0)) {
-            const __nv_bfloat16* src = p.aux + static_cast<size_t>(row) * p.ld_aux + col0;
+          if (aux_now && !write_pre_only) {
             float a[32];
-            if (full_chunk) {
+            if (have_aux) {
 #pragma unroll
-              for (int i = 0; i < 32; i += 8) {
-                const uint4 pk = *reinterpret_cast<const uint4*>(src + i);
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+              for (int i = 0; i < 4; ++i) {
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&ac[i]);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   const float2 t = __bfloat1622float2(h[j]);
-                  a[i + 2 * j] = t.x; a[i + 2 * j + 1] = t.y;
+                  a[8 * i + 2 * j] = t.x; a[8 * i + 2 * j + 1] = t.y;
                 }
               }
             } else {
+              const __nv_bfloat16* src = p.aux + static_cast<size_t>(row) * p.ld_aux + col0;
 #pragma unroll
               for (int i = 0; i < 32; ++i) a[i] = (col0 + i < p.N) ? __bfloat162float(src[i]) : 0.f;
             }
@@ -392,7 +445,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (p.tma_store) {
             // staging write: 64-column chunk (cc / 64), 16-byte units (cc % 64) / 8 .. +3 of row `trow`, XOR-swizzled
-            uint8_t* rowp = stg + (cc >> 6) * 16384 + trow * 128;
+            uint8_t* rowp = stg + (dual ? 1 : (cc >> 6)) * 16384 + trow * 128;
             const int u0 = (cc & 63) >> 3;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -435,6 +488,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
+        if (p.stall != nullptr) st_cols += clock64() - tc0;
         if (pass == npass - 1) {
           // accumulator stage drained: hand it back to the MMA warp
           tc::tc_fence_before();
@@ -445,11 +499,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc::fence_proxy_async_smem();                       // generic-proxy staging writes -> visible to the TMA
           asm volatile("bar.sync %0, 128;" ::"r"(nbar) : "memory");
           if (issuer) {
-            const CUtensorMap* tm = write_pre_only ? &tmC2 : &tmC;
+            if (dual) {
+              const int cbase = gcol0 + pass * 64;
+              if (cbase < p.N) {
+                tc::tma_store_2d(&tmC2, stg, cbase, m0);
+                tc::tma_store_2d(&tmC, stg + 16384, cbase, m0);
+              }
+            } else {
+              const CUtensorMap* tm = write_pre_only ? &tmC2 : &tmC;
 #pragma unroll
-            for (int c = 0; c < OUT_CHUNKS; ++c) {
-              const int cbase = n0 + half * COLS_PER_GROUP + c * 64;
-              if (cbase < p.N) tc::tma_store_2d(tm, stg + c * 16384, cbase, m0);   // rows >= M / cols >= N are clipped
+              for (int c = 0; c < OUT_CHUNKS; ++c) {
+                const int cbase = gcol0 + c * 64;
+                if (cbase < p.N) tc::tma_store_2d(tm, stg + c * 16384, cbase, m0);   // rows >= M / cols >= N are clipped
+              }
             }
             tc::tma_store_commit();
           }
@@ -458,7 +520,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     if (p.tma_store && issuer) tc::tma_store_wait<0>();        // all bulk stores complete before the CTA exits
-    if (p.stall != nullptr && warp == 2 && lane == 0) p.stall[blockIdx.x * 4 + 3] = st_tfull;
+    if (p.stall != nullptr && warp == 2 && lane == 0) { p.stall[blockIdx.x * 8 + 3] = st_tfull; p.stall[blockIdx.x * 8 + 4] = st_stage; p.stall[blockIdx.x * 8 + 5] = st_cols; }
   }
 
   tc::tc_fence_before();

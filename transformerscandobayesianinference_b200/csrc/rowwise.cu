@@ -41,6 +41,27 @@ template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16*
   *reinterpret_cast<uint4*>(p) = pk;
 }
 
+// Raw (still packed) 8-element vectors: rows are requested one iteration ahead and unpacked when they are used, so a warp
+// keeps two rows of loads in flight (Little: ~44 KB per SM must be outstanding to cover HBM latency at 6.5 TB/s).
+template <typename T> struct Raw8;
+template <> struct Raw8<float> { float4 a, b; };
+template <> struct Raw8<__nv_bfloat16> { uint4 a; };
+__device__ __forceinline__ void load_raw8(const float* p, Raw8<float>& r) {
+  r.a = *reinterpret_cast<const float4*>(p); r.b = *reinterpret_cast<const float4*>(p + 4);
+}
+__device__ __forceinline__ void load_raw8(const __nv_bfloat16* p, Raw8<__nv_bfloat16>& r) { r.a = *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void unpack8(const Raw8<float>& r, float (&v)[8]) {
+  v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+}
+__device__ __forceinline__ void unpack8(const Raw8<__nv_bfloat16>& r, float (&v)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r.a);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = __bfloat1622float2(h[j]);
+    v[2 * j] = t.x; v[2 * j + 1] = t.y;
+  }
+}
+
 // --------------------------------------------------------------------------------------------
 // Embedding forward: out[row,:] = x[row,:] Wx^T + bx + (t < sep ? y[row] wy + by : 0)
 // --------------------------------------------------------------------------------------------
@@ -129,14 +150,32 @@ layernorm_fwd_kernel(const T* __restrict__ z, int ldz, const float* __restrict__
   const int lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const float inv_e = 1.0f / static_cast<float>(E);
+  Raw8<T> nxt[NCH];
+  if (warp < rows) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int col = (c * 32 + lane) * 8;
+      if (col < E) load_raw8(z + static_cast<size_t>(warp) * ldz + col, nxt[c]);
+    }
+  }
   for (int row = warp; row < rows; row += nwarps) {
     float v[NCH][8];
     float s = 0.f;
+    Raw8<T> cur[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) cur[c] = nxt[c];
+    if (row + nwarps < rows) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int col = (c * 32 + lane) * 8;
+        if (col < E) load_raw8(z + static_cast<size_t>(row + nwarps) * ldz + col, nxt[c]);
+      }
+    }
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int col = (c * 32 + lane) * 8;
       if (col < E) {
-        load8<T>(z + static_cast<size_t>(row) * ldz + col, v[c]);
+        unpack8(cur[c], v[c]);
 #pragma unroll
         for (int i = 0; i < 8; ++i) s += v[c][i];
       } else {
@@ -204,8 +243,35 @@ layernorm_bwd_kernel(const T* __restrict__ dh, int lddh, const T* __restrict__ z
     }
   }
 
+  Raw8<T> nd[NCH], nz[NCH];
+  float nmean = 0.f, nrstd = 0.f;
+  if (warp < rows) {
+    nmean = mean_in[warp]; nrstd = rstd_in[warp];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int col = (c * 32 + lane) * 8;
+      if (col < E) {
+        load_raw8(dh + static_cast<size_t>(warp) * lddh + col, nd[c]);
+        load_raw8(z + static_cast<size_t>(warp) * ldz + col, nz[c]);
+      }
+    }
+  }
   for (int row = warp; row < rows; row += nwarps) {
-    const float mean = mean_in[row], rstd = rstd_in[row];
+    const float mean = nmean, rstd = nrstd;
+    Raw8<T> cd[NCH], cz[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) { cd[c] = nd[c]; cz[c] = nz[c]; }
+    if (row + nwarps < rows) {       // next row's loads go out before this row's reductions
+      nmean = mean_in[row + nwarps]; nrstd = rstd_in[row + nwarps];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int col = (c * 32 + lane) * 8;
+        if (col < E) {
+          load_raw8(dh + static_cast<size_t>(row + nwarps) * lddh + col, nd[c]);
+          load_raw8(z + static_cast<size_t>(row + nwarps) * ldz + col, nz[c]);
+        }
+      }
+    }
     float xh[NCH][8], g[NCH][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -213,8 +279,8 @@ layernorm_bwd_kernel(const T* __restrict__ dh, int lddh, const T* __restrict__ z
       const int col = (c * 32 + lane) * 8;
       if (col < E) {
         float d[8], zz[8];
-        load8<T>(dh + static_cast<size_t>(row) * lddh + col, d);
-        load8<T>(z + static_cast<size_t>(row) * ldz + col, zz);
+        unpack8(cd[c], d);
+        unpack8(cz[c], zz);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           xh[c][i] = (zz[i] - mean) * rstd;
