@@ -178,3 +178,22 @@ def test_install_dropin_registers_reference_module_names():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_wgrad_split_factors_fill_the_grid_once():
+    """engine._wgrad_splits: one round of work items over the persistent grid (measured optimum, tools/sweep_wgrad_splits.py)."""
+    from transformerscandobayesianinference_b200 import _lib, engine
+    saved = _lib._NUM_SMS
+    _lib._NUM_SMS = 148
+    try:
+        n = 512000
+        assert engine._wgrad_splits(n, 1536, 512) == 6      # in-proj: 6 x 2 pair tiles
+        assert engine._wgrad_splits(n, 1024, 512) == 9      # linear1
+        assert engine._wgrad_splits(n, 512, 1024) == 9      # linear2
+        assert engine._wgrad_splits(n, 512, 512) == 18      # out-proj
+        assert engine._wgrad_splits(64, 512, 512) == 1      # tiny contraction: never split
+        for rows, cols in ((1536, 512), (100, 1024), (1024, 100), (512, 1)):
+            ks = engine._wgrad_splits(n, rows, cols)
+            assert 1 <= ks <= (n // 64) // 8
+    finally:
+        _lib._NUM_SMS = saved

@@ -58,7 +58,18 @@ EXPORTED_SYMBOLS = [
 
 _lib = None
 _launches = 0          # kernel launches issued through this binding (bench.py reports it as gpu_launches)
-PROFILE_GEMM = None    # when a list: (flops, start_event, end_event) is appended for every tcgen05 GEMM launch
+PROFILE_GEMM = None    # when a list: (flops, start_event, end_event, algorithmic operand+result bytes) is appended for every tcgen05 GEMM launch
+
+
+_NUM_SMS = None
+
+
+def num_sms():
+    """SM count of the current device as the library sees it (grid sizing of the persistent kernels)."""
+    global _NUM_SMS
+    if _NUM_SMS is None:
+        _NUM_SMS = int(load().pfn_num_sms())
+    return _NUM_SMS
 
 
 def reset_launch_count():
@@ -177,7 +188,9 @@ def gemm(A, B, C, *, a_mn_major=False, b_mn_major=False, bias=None, aux=None, C2
             e0.record()
             check(lib.pfn_gemm_bf16_tc(ctypes.byref(d), stream_ptr()), "pfn_gemm_bf16_tc")
             e1.record()
-            PROFILE_GEMM.append((2.0 * M * N * K, e0, e1))
+            esz = 4 if C.dtype == torch.float32 else 2
+            nbytes = 2.0 * (M * K + N * K) + esz * M * N * (2 if C2 is not None else 1) + (2.0 * M * N if aux is not None else 0.0)
+            PROFILE_GEMM.append((2.0 * M * N * K, e0, e1, nbytes))
         else:
             check(lib.pfn_gemm_bf16_tc(ctypes.byref(d), stream_ptr()), "pfn_gemm_bf16_tc")
     else:

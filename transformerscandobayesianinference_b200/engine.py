@@ -34,10 +34,18 @@ def act_dtype(precision):
 
 
 def _wgrad_splits(n_tokens, out_rows, out_cols):
-    """k-splits so that tiles * splits ~ fills the SMs a few times over (contraction runs over the tokens)."""
-    tiles = ((out_rows + 127) // 128) * ((out_cols + 255) // 256 if out_cols > 128 else 1)
+    """Split-K factor of a wgrad GEMM (contraction over the tokens): ONE round of work items over the persistent grid.
+
+    Measured (tools/sweep_wgrad_splits.py, B200): the best factor is the one that gives ~one work item per CTA pair --
+    more splits only add fp32 atomic traffic on the same [out_rows, out_cols] block (qkv 6: 0.59 ms vs 24: 0.62;
+    mlp 9: 0.39 vs 37: 0.45; out-proj 18: 0.22 vs 74: 0.29)."""
+    sms = L.num_sms()
+    if out_cols > 128:      # cta_group::2 path: 256 x 256 tiles, one per CTA pair
+        tiles, units = ((out_rows + 255) // 256) * ((out_cols + 255) // 256), max(sms // 2, 1)
+    else:                   # single-CTA 128 x 128 tiles
+        tiles, units = ((out_rows + 127) // 128) * ((out_cols + 127) // 128), sms
     num_kb = (n_tokens + 63) // 64
-    want = max(1, (4 * 148) // max(tiles, 1))
+    want = max(1, units // max(tiles, 1))
     return max(1, min(want, num_kb // 8 if num_kb >= 16 else 1))
 
 
