@@ -236,18 +236,20 @@ def run_engine(args):
     g_ms = sum(r[1].elapsed_time(r[2]) for r in gemm_prof)
     gemm_tf = g_flops / (g_ms / 1e3) / 1e12 if g_ms > 0 else None
     # DRAM traffic of the same kernel from the committed `ncu --set full` capture of this command (profiles/, not measured live)
-    traffic, traffic_src = None, None
+    traffic, traffic_src, traffic_alg = None, None, None
     tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_gemm_traffic.json")
     if os.path.exists(tpath) and B == CFG2["batch"] and args.precision == "bf16":
         with open(tpath) as f:
             tj = json.load(f)
         traffic, traffic_src = tj["mean_dram_bytes_per_launch"], "profiles/r1_gemm_traffic.json"
+        traffic_alg = tj.get("mean_algorithmic_bytes_per_launch")
     g_bytes = sum(r[3] for r in gemm_prof)
     roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM, all launches of the timed steps)",
                 "achieved": gemm_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": (gemm_tf / peaks["bf16_sustained"]) if gemm_tf else None,
                 "traffic": traffic, "traffic_unit": "bytes/launch (dram read+write, mean over the captured launches)",
-                "traffic_source": traffic_src, "algorithmic_bytes_per_launch": g_bytes / max(len(gemm_prof), 1),
+                "traffic_source": traffic_src, "traffic_algorithmic": traffic_alg,   # same 8 captured launches: operands + results once
+                "algorithmic_bytes_per_launch": g_bytes / max(len(gemm_prof), 1),   # mean over ALL launches of the timed steps
                 "launches": len(gemm_prof), "kernel_ms_per_step": g_ms / args.steps, "peak_source": peaks["source"] + ", sustained bf16",
                 "step": {"achieved": achieved_step, "frac": achieved_step / peaks["bf16_sustained"], "flops_per_step": flops}}
 
