@@ -95,3 +95,32 @@ def test_attention_tc_bwd(cuda_device, T, B, H, sep):
         err = (got[:, sl] - want).abs().max().item()
         scale_all = qr.grad.abs().max().item()
         assert err <= 3e-2 * want.abs().max().item() + 1e-3 * scale_all, f"{name}: err {err} vs scale {want.abs().max().item()}"
+
+
+def test_attention_tc_bwd_pair_variant_matches_default(cuda_device):
+    """The opt-in tile-pair dQ kernel (PFN_ATTN_DQ_PAIR=1, read once per process) must give the default kernel's dqkv."""
+    import os, subprocess, sys, tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = (
+        "import sys, torch; sys.path.insert(0, %r)\n"
+        "from transformerscandobayesianinference_b200 import _lib as L\n"
+        "torch.manual_seed(5); dev = torch.device('cuda:0'); outs = []\n"
+        "for (T, B, H, sep) in [(300, 2, 2, 150), (513, 1, 1, 257), (640, 1, 2, 0)]:\n"
+        "    E = H * 128\n"
+        "    qkv = torch.randn(T * B, 3 * E, device=dev).to(torch.bfloat16)\n"
+        "    out = torch.empty(T * B, E, device=dev, dtype=torch.bfloat16); lse = torch.empty(B * H, T, device=dev)\n"
+        "    L.attention_fwd(qkv, out, lse, T, B, H, 128, sep, use_tc=True)\n"
+        "    dout = torch.randn(T * B, E, device=dev).to(torch.bfloat16); dqkv = torch.zeros_like(qkv); delta = torch.empty_like(lse)\n"
+        "    L.attention_bwd(qkv, out, lse, dout, dqkv, delta, T, B, H, 128, sep, use_tc=True)\n"
+        "    outs.append(dqkv.float().cpu())\n"
+        "torch.save(outs, sys.argv[1])\n" % root)
+    res = {}
+    with tempfile.TemporaryDirectory() as td:
+        for flag in ("0", "1"):
+            path = os.path.join(td, f"dq{flag}.pt")
+            subprocess.run([sys.executable, "-c", script, path], check=True, timeout=300,
+                           env=dict(os.environ, PFN_ATTN_DQ_PAIR=flag))
+            res[flag] = torch.load(path)
+    for a, b in zip(res["0"], res["1"]):
+        assert torch.isfinite(b).all()
+        assert (a - b).abs().max().item() <= 2e-2 * (a.abs().max().item() + 1e-6)
