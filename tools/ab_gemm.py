@@ -25,7 +25,19 @@ for (Nn, K, bmn, name) in [(1024, 512, 0, "plain"), (1024, 512, 0, "gelu+c2"), (
     if name == "gelu+c2": kw = dict(bias=torch.randn(Nn, device=dev), C2=torch.empty_like(C), epilogue=1)
     elif name == "gelu'": kw = dict(aux=torch.randn(N, Nn, device=dev).to(torch.bfloat16), epilogue=2)
     elif name.startswith("+aux"): kw = dict(bias=torch.randn(Nn, device=dev), aux=torch.randn(N, Nn, device=dev).to(torch.bfloat16))
-    out.append(f"{name} {t(lambda: L.gemm(A, Bm, C, b_mn_major=bool(bmn), M=N, N=Nn, K=K, use_tc=True, **kw)):.3f}")
+    ms = t(lambda: L.gemm(A, Bm, C, b_mn_major=bool(bmn), M=N, N=Nn, K=K, use_tc=True, **kw))
+    extra = ""
+    if name in ("gelu+c2", "gelu'"):
+        R = 4096
+        acc = A[:R].float() @ (Bm.float() if bmn else Bm.float().t())
+        if name == "gelu+c2":
+            ref = torch.nn.functional.gelu(acc + kw["bias"])
+        else:
+            u = kw["aux"][:R].float()
+            ref = acc * (0.5 * (1 + torch.erf(u / 2 ** 0.5)) + u * torch.exp(-0.5 * u * u) / (2 * 3.141592653589793) ** 0.5)
+        err = (C[:R].float() - ref).abs().max().item() / ref.abs().max().item()
+        extra = f" (err {err:.1e})"
+    out.append(f"{name} {ms:.3f}{extra}")
 print(" | ".join(out))
 '''.replace("HERE", repr(HERE))
 variants = sys.argv[1:] or ["tanh1", "logi1", "tanh2", "logi1nopf"]

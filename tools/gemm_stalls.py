@@ -28,4 +28,4 @@ for (M, Nn, K, amn, bmn, name) in CASES:
     L.load().pfn_debug_attention_trace(None, 0, 0)
     st = buf.view(148, 8).double().mean(0).tolist()
     ms = e0.elapsed_time(e1)
-    print(f"{name}: {ms:.3f} ms | mean clocks per CTA waiting: producer(empty) {st[0]:.0f}, MMA(full) {st[1]:.0f}, MMA(tempty) {st[2]:.0f}, epilogue(tfull) {st[3]:.0f}, epilogue(staging free) {st[4]:.0f}, epilogue(column loop) {st[5]:.0f}")
+    print(f"{name}: {ms:.3f} ms | mean clocks per CTA waiting: producer(empty) {st[0]:.0f}, MMA(full) {st[1]:.0f}, MMA(tempty) {st[2]:.0f}, epilogue(tfull) {st[3]:.0f}, epilogue(staging free) {st[4]:.0f}, epilogue(column loop) {st[5]:.0f} of which tmem ld wait {st[6]:.0f}")

@@ -97,6 +97,36 @@ __device__ __forceinline__ float fast_tanh(float x) {
   return y;
 }
 constexpr float kGeluC0 = 0.7974228190582262f, kGeluC1 = 0.0370038563083048f, kGeluC2 = -0.0003475408844912201f;
+#ifdef PFN_GELU_TANH_F16X2
+// A/B variant (NOT the default; measured 0.81 ms GELU / 0.77 ms GELU' vs 0.72 / 0.77 for the default pair, so halving the
+// MUFU count buys nothing: the epilogue is not MUFU-bound): the transcendental runs on PAIRS of elements as
+// tanh.approx.f16x2 (one MUFU op per two elements; the argument
+// |u q| <= ~14 and the result in [-1, 1] are comfortably inside fp16, its 2^-11 relative error matches tanh.approx.f32).
+__device__ __forceinline__ void gelu_tanh_pair(float za, float zb, float& ta, float& tb) {
+  uint32_t packed, res;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(packed) : "f"(zb), "f"(za));      // low half = za, high half = zb
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(res) : "r"(packed));
+  asm("{\n\t.reg .f16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}" : "=f"(ta), "=f"(tb) : "r"(res));
+}
+__device__ __forceinline__ void gelu_fast2(float& a, float& b) {
+  const float a2 = fminf(a * a, 80.0f), b2 = fminf(b * b, 80.0f);
+  float ta, tb;
+  gelu_tanh_pair(a * fmaf(a2, fmaf(a2, kGeluC2, kGeluC1), kGeluC0), b * fmaf(b2, fmaf(b2, kGeluC2, kGeluC1), kGeluC0), ta, tb);
+  const float ha = 0.5f * a, hb = 0.5f * b;
+  a = fmaf(ha, ta, ha);
+  b = fmaf(hb, tb, hb);
+}
+// returns GELU'(a), GELU'(b)
+__device__ __forceinline__ void gelu_grad_fast2(float& a, float& b) {
+  const float a2 = fminf(a * a, 80.0f), b2 = fminf(b * b, 80.0f);
+  float ta, tb;
+  gelu_tanh_pair(a * fmaf(a2, fmaf(a2, kGeluC2, kGeluC1), kGeluC0), b * fmaf(b2, fmaf(b2, kGeluC2, kGeluC1), kGeluC0), ta, tb);
+  const float da = fmaf(a2, fmaf(a2, 2.5f * kGeluC2, 1.5f * kGeluC1), 0.5f * kGeluC0);
+  const float db = fmaf(b2, fmaf(b2, 2.5f * kGeluC2, 1.5f * kGeluC1), 0.5f * kGeluC0);
+  a = fmaf(a * da, fmaf(-ta, ta, 1.0f), fmaf(0.5f, ta, 0.5f));
+  b = fmaf(b * db, fmaf(-tb, tb, 1.0f), fmaf(0.5f, tb, 0.5f));
+}
+#endif
 // Measured A/B on one B200 (tools/ab_gemm.py, 512000x1024x512): GELU epilogue 0.735 ms with the exp/rcp form vs 0.808 ms with
 // tanh.approx; GELU' epilogue 0.766 ms with tanh.approx vs 0.822 ms with exp/rcp -- so each uses the form that won.
 constexpr float kGeluK = -2.8853900817779268f;   // -2 log2(e)

@@ -46,7 +46,7 @@ struct GemmTcParams {
   int kb_per_split;              // k-blocks (of 64) per split
   int tiles_m, tiles_n;
   int l2_prefetch;               // 1 => the producer prefetches the next work item's A tile into L2
-  long long* stall;              // debug: per-CTA [8] clock sums: producer wait-empty, MMA wait-full, MMA wait-tempty, epilogue wait-tfull, epilogue wait-staging (store read + group barrier), epilogue column loop
+  long long* stall;              // debug: per-CTA [8] clock sums: producer wait-empty, MMA wait-full, MMA wait-tempty, epilogue wait-tfull, epilogue wait-staging (store read + group barrier), epilogue column loop, of which tcgen05.wait::ld
   int tma_store;                 // 1 => bf16 C (and C2) leave through the smem staging buffer + TMA store
 };
 
@@ -296,7 +296,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool two_pass = gelu_c2 && !dual;
     const bool use_aux = p.aux != nullptr;
     bool store_pending = false;
-    long long st_tfull = 0, st_stage = 0, st_cols = 0;
+    long long st_tfull = 0, st_stage = 0, st_cols = 0, st_ldw = 0;
     int it = 0;
     for (int w = work0; w < total_work; w += work_stride, ++it) {
       const int split = w / tiles;
@@ -362,7 +362,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int cc = cc_begin; cc < cc_end; cc += 32) {
           const int col0 = gcol0 + cc;
           if (col0 >= p.N) break;  // warp-uniform
-          tc::tmem_ld_wait();
+          if (p.stall != nullptr) { const long long t0 = clock64(); tc::tmem_ld_wait(); st_ldw += clock64() - t0; }
+          else tc::tmem_ld_wait();
           float f[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
@@ -415,8 +416,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   if (col0 + i < p.N) dst[i] = __float2bfloat16_rn(f[i]);
               }
             }
+#ifdef PFN_GELU_TANH_F16X2
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) gelu_fast2(f[i], f[i + 1]);
+#else
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = gelu_fast(f[i]);
+#endif
           }
           if (aux_now && !write_pre_only) {
             float a[32];
@@ -436,8 +442,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int i = 0; i < 32; ++i) a[i] = (col0 + i < p.N) ? __bfloat162float(src[i]) : 0.f;
             }
             if (p.act == PFN_EPI_GELU_BWD) {
+#ifdef PFN_GELU_TANH_F16X2
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                gelu_grad_fast2(a[i], a[i + 1]);
+                f[i] *= a[i]; f[i + 1] *= a[i + 1];
+              }
+#else
 #pragma unroll
               for (int i = 0; i < 32; ++i) f[i] *= gelu_grad_fast(a[i]);
+#endif
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i) f[i] += a[i];
@@ -520,7 +534,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     if (p.tma_store && issuer) tc::tma_store_wait<0>();        // all bulk stores complete before the CTA exits
-    if (p.stall != nullptr && warp == 2 && lane == 0) { p.stall[blockIdx.x * 8 + 3] = st_tfull; p.stall[blockIdx.x * 8 + 4] = st_stage; p.stall[blockIdx.x * 8 + 5] = st_cols; }
+    if (p.stall != nullptr && warp == 2 && lane == 0) { p.stall[blockIdx.x * 8 + 3] = st_tfull; p.stall[blockIdx.x * 8 + 4] = st_stage; p.stall[blockIdx.x * 8 + 5] = st_cols; p.stall[blockIdx.x * 8 + 6] = st_ldw; }
   }
 
   tc::tc_fence_before();
