@@ -211,8 +211,11 @@ layernorm_fwd_kernel(const T* __restrict__ z, int ldz, const float* __restrict__
   }
 }
 
+#ifndef PFN_LN_BWD_MIN_CTAS
+#define PFN_LN_BWD_MIN_CTAS 1
+#endif
 template <typename T, int NCH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, PFN_LN_BWD_MIN_CTAS)
 layernorm_bwd_kernel(const T* __restrict__ dh, int lddh, const T* __restrict__ z, int ldz,
                      const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                      const float* __restrict__ gamma, T* __restrict__ dz, int lddz, float* __restrict__ dgamma,
