@@ -246,35 +246,33 @@ layernorm_bwd_kernel(const T* __restrict__ dh, int lddh, const T* __restrict__ z
     }
   }
 
-  Raw8<T> nd[NCH], nz[NCH];
-  float nmean = 0.f, nrstd = 0.f;
-  if (warp < rows) {
-    nmean = mean_in[warp]; nrstd = rstd_in[warp];
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      const int col = (c * 32 + lane) * 8;
-      if (col < E) {
-        load_raw8(dh + static_cast<size_t>(warp) * lddh + col, nd[c]);
-        load_raw8(z + static_cast<size_t>(warp) * ldz + col, nz[c]);
-      }
-    }
-  }
-  for (int row = warp; row < rows; row += nwarps) {
-    const float mean = nmean, rstd = nrstd;
-    Raw8<T> cd[NCH], cz[NCH];
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) { cd[c] = nd[c]; cz[c] = nz[c]; }
-    if (row + nwarps < rows) {       // next row's loads go out before this row's reductions
-      nmean = mean_in[row + nwarps]; nrstd = rstd_in[row + nwarps];
+  // The kernel needs ~190 registers (three column accumulators per lane), i.e. ONE 8-warp CTA per SM: occupancy cannot
+  // supply the bytes in flight, so every warp keeps TWO rows of loads outstanding beyond the one it is reducing
+  // (2 CTAs/SM via __launch_bounds__(256, 2) spills and halves the bandwidth: tools/ab_rowwise.py).
+  Raw8<T> nd[NCH], nz[NCH], md[NCH], mz[NCH];      // row + nwarps, row + 2 nwarps
+  float nmean = 0.f, nrstd = 0.f, mmean = 0.f, mrstd = 0.f;
+  auto request = [&](int r, Raw8<T> (&rd)[NCH], Raw8<T> (&rz)[NCH], float& rm, float& rs) {
+    if (r < rows) {
+      rm = mean_in[r]; rs = rstd_in[r];
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         const int col = (c * 32 + lane) * 8;
         if (col < E) {
-          load_raw8(dh + static_cast<size_t>(row + nwarps) * lddh + col, nd[c]);
-          load_raw8(z + static_cast<size_t>(row + nwarps) * ldz + col, nz[c]);
+          load_raw8(dh + static_cast<size_t>(r) * lddh + col, rd[c]);
+          load_raw8(z + static_cast<size_t>(r) * ldz + col, rz[c]);
         }
       }
     }
+  };
+  request(warp, nd, nz, nmean, nrstd);
+  request(warp + nwarps, md, mz, mmean, mrstd);
+  for (int row = warp; row < rows; row += nwarps) {
+    const float mean = nmean, rstd = nrstd;
+    Raw8<T> cd[NCH], cz[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) { cd[c] = nd[c]; cz[c] = nz[c]; nd[c] = md[c]; nz[c] = mz[c]; }
+    nmean = mmean; nrstd = mrstd;
+    request(row + 2 * nwarps, md, mz, mmean, mrstd);      // goes out before this row's reductions
     float xh[NCH][8], g[NCH][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
