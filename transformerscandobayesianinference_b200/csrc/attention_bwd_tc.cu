@@ -366,22 +366,6 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     tc::KernelTrace tr = tc::trace_make(p.trace, p.trace_cap, warp);   // one region per elementwise warp (2..9)
     uint32_t g = 0, tcount = 0;
-    // Row statistics of the NEXT tile are requested while this tile is processed: at a tile boundary the first score block
-    // is ready long before a fresh global load of lse / delta would return (11-15 % of the row threads' stall samples in
-    // the ncu source view sat on exactly that load).
-    auto stat_request = [&](int ww, float& l_raw, float& d_raw) {
-      l_raw = 0.f; d_raw = 0.f;
-      if (ww < p.total_work) {
-        const int bh2 = ww / p.n_tiles;
-        const int i2 = (ww - bh2 * p.n_tiles) * 128 + row;
-        if (i2 < p.T) {
-          l_raw = __ldg(p.lse + static_cast<size_t>(bh2) * p.T + i2);
-          d_raw = __ldg(p.delta + static_cast<size_t>(bh2) * p.T + i2);
-        }
-      }
-    };
-    float lse_next, delta_next;
-    stat_request(blockIdx.x, lse_next, delta_next);
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
       const int bh = w / p.n_tiles;
       const int qt = w - bh * p.n_tiles;
@@ -393,9 +377,11 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
       int dstart[2];
       const int nb = ab_tile_block_plan(i0, p.sep, p.T, nblk, dstart);
       tc::mbar_wait(qdo_full, tcount & 1);     // acquire the TMA-written Q / dO tiles (rows are read back in diagonal blocks)
-      const float lse2 = valid ? lse_next * 1.4426950408889634f : INFINITY;
-      const float dls = valid ? delta_next * p.scale : 0.f;              // delta * scale
-      stat_request(w + gridDim.x, lse_next, delta_next);                 // in flight during this tile
+      float lse2 = INFINITY, dls = 0.f;       // dls = delta * scale
+      if (valid) {
+        lse2 = p.lse[static_cast<size_t>(bh) * p.T + i] * 1.4426950408889634f;
+        dls = p.delta[static_cast<size_t>(bh) * p.T + i] * p.scale;
+      }
       for (int j = 0; j < nb; ++j, ++g) {
         const uint32_t buf = g % 3;
         tc::mbar_wait(&s_full[buf], (g / 3) & 1);
