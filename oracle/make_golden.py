@@ -27,6 +27,30 @@ MODEL_CASES = {
 }
 
 
+# BASELINE.json configurations at their MODEL shape (sequence length, width, depth, heads, bars, single_eval_pos) with a
+# small batch so the unmodified reference finishes in seconds on CPU; the per-sequence maths is batch-invariant.
+# `head`: "bar" = FullSupportBarDistribution, "bce" = BCEWithLogitsLoss on a binarised target (cfg 3, train.py:84-85).
+CONFIG_CASES = {
+    "cfg1_b64": dict(T=50, B=64, F=1, E=128, nhid=256, L=2, H=4, n_out=100, sep=25, seed=101, head="bar"),
+    "cfg2_b4": dict(T=1000, B=4, F=1, E=512, nhid=1024, L=6, H=4, n_out=100, sep=500, seed=102, head="bar"),
+    "cfg3_b4_bar": dict(T=512, B=4, F=18, E=512, nhid=1024, L=12, H=4, n_out=100, sep=256, seed=103, head="bar"),
+    "cfg3_b4_bce": dict(T=512, B=4, F=18, E=512, nhid=1024, L=12, H=4, n_out=1, sep=256, seed=104, head="bce"),
+    "cfg4_b2": dict(T=2000, B=2, F=1, E=512, nhid=1024, L=6, H=4, n_out=100, sep=1000, seed=105, head="bar"),
+}
+N_PROBE = 96   # gradient elements stored per parameter tensor (seeded positions), for per-element comparisons
+
+
+def grad_probe_index(numel, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(0, numel, (min(N_PROBE, numel),), generator=g)
+
+
+def case_targets(case, y):
+    """Targets of the query rows: y itself for the bar head, a binarised y for the BCE head."""
+    t = y[case["sep"]:]
+    return (t > 0).float() if case.get("head") == "bce" else t
+
+
 def _load_ref(name):
     if REF not in sys.path:
         sys.path.insert(0, REF)
@@ -110,6 +134,39 @@ def main():
             "torch_version": str(torch.__version__),
         }, os.path.join(OUT, f"model_{name}.pt"))
         print(name, "loss", float(loss))
+
+    # ---- BASELINE.json configurations at model shape: loss, logits, grad norms and seeded per-element gradient probes
+    for name, case in CONFIG_CASES.items():
+        ctor = lambda enc, yenc: ref_transformer.TransformerModel(enc, case["n_out"], case["E"], case["H"], case["nhid"],
+                                                                  case["L"], 0.0, y_encoder=yenc)
+        model = build_case_weights(ctor, case)
+        x, y = case_inputs(case)
+        model.train()
+        logits = model((x, y), single_eval_pos=case["sep"])
+        targets = case_targets(case, y)
+        if case["head"] == "bar":
+            crit = ref_bar.FullSupportBarDistribution(case_borders(case))
+            losses = crit(logits.reshape(-1, case["n_out"]), targets.flatten()).view(*logits.shape[:2])
+        else:
+            crit = torch.nn.BCEWithLogitsLoss(reduction='none')
+            losses = crit(logits.flatten(), targets.flatten()).view(*logits.shape[:2])
+        loss = losses.mean()
+        loss.backward()
+        probes = {}
+        for i, (k, p) in enumerate(model.named_parameters()):
+            idx = grad_probe_index(p.numel(), case["seed"] * 1000 + i)
+            probes[k] = (idx, p.grad.flatten()[idx].clone())
+        torch.save({
+            "case": case,
+            "weights_checksum": checksum(model.state_dict()),
+            "logits": logits.detach().to(torch.float32), "losses": losses.detach(), "loss": loss.detach(),
+            "grad_checksum": {k: (float(p.grad.double().sum()), float(p.grad.double().abs().sum()), float(p.grad.double().norm()),
+                                  float(p.grad.double().abs().max()))
+                              for k, p in model.named_parameters()},
+            "grad_probes": probes,
+            "torch_version": str(torch.__version__),
+        }, os.path.join(OUT, f"model_{name}.pt"))
+        print(name, "loss", float(loss), flush=True)
 
     # ---- bar distribution (bar_distribution.py:19-117) incl. edge cases
     g = torch.Generator().manual_seed(42)

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 from transformerscandobayesianinference_b200 import bar_distribution, transformer
 from oracle import pfn_oracle as O
-from oracle.make_golden import MODEL_CASES, build_case_weights, case_inputs, case_borders
+from oracle.make_golden import MODEL_CASES, CONFIG_CASES, build_case_weights, case_inputs, case_borders, case_targets
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -66,6 +66,65 @@ def test_bf16_engine_matches_reference_golden(cuda_device, name):
         s, a, nrm = gold["grad_checksum"][k]
         got = p.grad.float().cpu()
         assert abs(got.norm().item() - nrm) <= 6e-2 * nrm + 1e-5, f"{k}: grad norm {got.norm().item()} vs {nrm}"
+
+
+def _run_config_case(case, precision, dev):
+    model = _model(case, precision, dev)
+    x, y = case_inputs(case)
+    t = case_targets(case, y).to(dev)
+    x, y = x.to(dev), y.to(dev)
+    model.train()
+    logits = model((x, y), single_eval_pos=case["sep"])
+    if case["head"] == "bar":
+        crit = bar_distribution.FullSupportBarDistribution(case_borders(case)).to(dev)
+        losses = crit(logits.reshape(-1, case["n_out"]), t.flatten()).view(*logits.shape[:2])
+    else:
+        losses = torch.nn.BCEWithLogitsLoss(reduction='none')(logits.flatten(), t.flatten()).view(*logits.shape[:2])
+    loss = losses.mean()
+    loss.backward()
+    return model, logits, losses, loss
+
+
+@pytest.mark.parametrize("name", list(CONFIG_CASES))
+def test_fp32_engine_matches_reference_at_baseline_config_shapes(cuda_device, name):
+    """BASELINE.json configs 1-4 at their model shape (T, E, L, H, bars, sep; small batch): NLL within 1e-4 relative of the
+    unmodified reference, logits, gradient norms and seeded per-element gradient probes."""
+    gold = torch.load(os.path.join(GOLD, f"model_{name}.pt"))
+    case = gold["case"]
+    model, logits, losses, loss = _run_config_case(case, "fp32", cuda_device)
+    rel = abs(loss.item() - gold["loss"].item()) / abs(gold["loss"].item())
+    assert rel <= 1e-4, f"NLL rel err {rel}"
+    assert (logits.cpu().float() - gold["logits"]).abs().max().item() <= 1e-3 * gold["logits"].abs().max().item()
+    for k, p in model.named_parameters():
+        s, a, nrm, amax = gold["grad_checksum"][k]
+        got = p.grad.float().cpu()
+        assert abs(got.norm().item() - nrm) <= 3e-3 * nrm + 1e-7, f"{k}: grad norm {got.norm().item()} vs {nrm}"
+        idx, ref = gold["grad_probes"][k]
+        assert (got.flatten()[idx] - ref).abs().max().item() <= 3e-3 * amax + 1e-8, k
+
+
+@pytest.mark.parametrize("name", list(CONFIG_CASES))
+def test_bf16_engine_matches_reference_at_baseline_config_shapes(cuda_device, name):
+    """Same cases on the bf16 tensor-core engine: NLL within 1e-2 relative; gradients per tensor (norm) AND per element
+    (seeded probes: every probed element within 8 % of the tensor's largest gradient, probe vector within 6 % in L2)."""
+    gold = torch.load(os.path.join(GOLD, f"model_{name}.pt"))
+    case = gold["case"]
+    model, logits, losses, loss = _run_config_case(case, "bf16", cuda_device)
+    rel = abs(loss.item() - gold["loss"].item()) / abs(gold["loss"].item())
+    assert rel <= 1e-2, f"NLL rel err {rel}"
+    worst = (0.0, 0.0, "")
+    for k, p in model.named_parameters():
+        s, a, nrm, amax = gold["grad_checksum"][k]
+        got = p.grad.float().cpu()
+        assert abs(got.norm().item() - nrm) <= 6e-2 * nrm + 1e-5, f"{k}: grad norm {got.norm().item()} vs {nrm}"
+        idx, ref = gold["grad_probes"][k]
+        d = got.flatten()[idx] - ref
+        e_max = d.abs().max().item() / (amax + 1e-12)
+        e_l2 = d.norm().item() / (ref.norm().item() + 1e-3 * nrm / got.numel() ** 0.5 * len(idx) ** 0.5 + 1e-12)
+        worst = max(worst, (e_max, e_l2, k))
+        assert e_max <= 8e-2, f"{k}: probe max err {e_max} of the tensor's largest gradient"
+        assert e_l2 <= 6e-2 or ref.norm().item() < 1e-2 * nrm * (len(idx) / got.numel()) ** 0.5, f"{k}: probe L2 err {e_l2}"
+    print(f"[{name}] bf16 NLL rel {rel:.2e}; worst gradient probe: max {worst[0]:.3f}, L2 {worst[1]:.3f} ({worst[2]})")
 
 
 def test_engine_matches_oracle_full_gradients(cuda_device):

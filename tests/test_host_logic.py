@@ -183,8 +183,8 @@ def test_install_dropin_registers_reference_module_names():
 def test_wgrad_split_factors_fill_the_grid_once():
     """engine._wgrad_splits: one round of work items over the persistent grid (measured optimum, tools/sweep_wgrad_splits.py)."""
     from transformerscandobayesianinference_b200 import _lib, engine
-    saved = _lib._NUM_SMS
-    _lib._NUM_SMS = 148
+    saved = _lib.num_sms
+    _lib.num_sms = lambda device=None: 148
     try:
         n = 512000
         assert engine._wgrad_splits(n, 1536, 512) == 6      # in-proj: 6 x 2 pair tiles
@@ -196,4 +196,4 @@ def test_wgrad_split_factors_fill_the_grid_once():
             ks = engine._wgrad_splits(n, rows, cols)
             assert 1 <= ks <= (n // 64) // 8
     finally:
-        _lib._NUM_SMS = saved
+        _lib.num_sms = saved

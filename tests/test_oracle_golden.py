@@ -82,3 +82,29 @@ def test_oracle_bar_distribution_matches_reference():
             assert (nf - e["nll_full"]).abs().max().item() <= 1e-5 * (e["nll_full"].abs().max().item() + 1)
             mf = O.bar_mean_ref(e["logits"], e["borders"], full_support=True)
             assert (mf - e["mean_full"]).abs().max().item() <= 1e-5
+
+
+# ---- BASELINE.json configurations at model shape (goldens from the unmodified reference, oracle/make_golden.py CONFIG_CASES)
+from oracle.make_golden import CONFIG_CASES, case_targets  # noqa: E402
+
+
+@pytest.mark.parametrize("name", list(CONFIG_CASES))
+def test_oracle_matches_reference_at_baseline_config_shapes(name):
+    gold = torch.load(os.path.join(GOLD, f"model_{name}.pt"))
+    case = gold["case"]
+    model = _ref_like_model(case)
+    cs = checksum(model.state_dict())
+    for k, (s, a) in gold["weights_checksum"].items():
+        assert abs(cs[k][0] - s) <= 1e-9 * (abs(s) + 1) and abs(cs[k][1] - a) <= 1e-9 * (a + 1), f"weights differ: {k}"
+    x, y = case_inputs(case)
+    P = O.params_from_state_dict(model.state_dict(), case["L"], torch.float64)
+    with torch.no_grad():
+        logits = O.transformer_forward_ref(P, x.double(), y.double(), case["sep"], case["H"])
+        assert (logits - gold["logits"].double()).abs().max().item() <= 3e-4 * gold["logits"].abs().max().item()
+        t = case_targets(case, y).flatten().double()
+        if case["head"] == "bar":
+            nll = O.bar_nll_ref(logits.reshape(-1, case["n_out"]), t, case_borders(case).double(), full_support=True)
+        else:
+            z = logits.flatten()
+            nll = torch.clamp(z, min=0) - z * t + torch.log1p(torch.exp(-z.abs()))     # BCE-with-logits, stable form
+        assert abs(nll.mean().item() - gold["loss"].item()) <= 1e-4 * abs(gold["loss"].item())

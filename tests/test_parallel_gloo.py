@@ -31,6 +31,28 @@ def _worker(rank, world, port, ret):
     ((ref(X) - Y) ** 2).mean().backward()
     for p, q in zip(params, ref.parameters()):
         assert torch.allclose(p.grad, q.grad, atol=1e-6)
+    # train.build_trainer under WORLD_SIZE=2: identical weights, DIFFERENT prior draws per rank (the ranks arrive with the
+    # same generator state), the local batch is global / world, the python `random` stream (single_eval_pos) stays shared
+    import random
+    import numpy as np
+    from transformerscandobayesianinference_b200 import encoders, priors, train as T_
+    torch.manual_seed(5); np.random.seed(5); random.seed(5)
+    tr = T_.build_trainer(priors.ridge.DataLoader, torch.nn.MSELoss(reduction='none'), encoders.Linear, emsize=16, nhid=32,
+                          nlayers=1, nhead=2, dropout=0.0, epochs=1, steps_per_epoch=2, batch_size=6, bptt=5, lr=1e-3,
+                          warmup_epochs=0, y_encoder_generator=encoders.Linear,
+                          extra_prior_kwargs_dict=dict(num_features=3), single_eval_pos_gen=2, gpu_device='cpu')
+    assert tr.dl.get_batch_kwargs['batch_size'] == 3
+    w = torch.cat([p.detach().flatten() for p in tr.model.parameters()])
+    ws = [torch.zeros_like(w) for _ in range(world)]
+    dist.all_gather(ws, w)
+    assert torch.equal(ws[0], ws[1])
+    (x, y), _ = tr.dl.gbm(**tr.dl.get_batch_kwargs, fuse_x_y=False)
+    xs_ = [torch.zeros_like(x) for _ in range(world)]
+    dist.all_gather(xs_, x.contiguous())
+    assert not torch.equal(xs_[0], xs_[1]), "ranks drew the same prior batch"
+    draws = [torch.zeros(2) for _ in range(world)]
+    dist.all_gather(draws, torch.tensor([random.random(), float(np.random.rand() )]))
+    assert draws[0][0] == draws[1][0] and draws[0][1] != draws[1][1]
     seps = parallel.broadcast_object([3, 1, 4] if rank == 0 else None)
     assert seps == [3, 1, 4]
     m = parallel.allreduce_mean_scalar(torch.tensor(float(rank)))

@@ -61,15 +61,16 @@ _launches = 0          # kernel launches issued through this binding (bench.py r
 PROFILE_GEMM = None    # when a list: (flops, start_event, end_event, algorithmic operand+result bytes) is appended for every tcgen05 GEMM launch
 
 
-_NUM_SMS = None
+_NUM_SMS = {}
 
 
-def num_sms():
-    """SM count of the current device as the library sees it (grid sizing of the persistent kernels)."""
-    global _NUM_SMS
-    if _NUM_SMS is None:
-        _NUM_SMS = int(load().pfn_num_sms())
-    return _NUM_SMS
+def num_sms(device=None):
+    """SM count of `device` (default: the current device) as the library sees it (grid sizing of the persistent kernels)."""
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index
+    if idx not in _NUM_SMS:
+        with torch.cuda.device(idx):
+            _NUM_SMS[idx] = int(load().pfn_num_sms())
+    return _NUM_SMS[idx]
 
 
 def reset_launch_count():
@@ -131,8 +132,31 @@ def check(rc, what):
         raise RuntimeError(f"{what} failed (rc={rc}): {msg.decode() if msg else 'no message'}")
 
 
-def stream_ptr():
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+def stream_ptr(device=None):
+    """torch's current stream ON `device` (not on whatever device happens to be current)."""
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class on_device:
+    """Make `device` the current CUDA device for the duration of a library call: the kernels launch on the current
+    device, so a call whose tensors live elsewhere (train(gpu_device='cuda:1'), a rank's own GPU) must switch first."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, device):
+        self.idx = device.index if device.index is not None else torch.cuda.current_device()
+        self.prev = None
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if cur != self.idx:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+        return False
 
 
 def dtype_code(t):
@@ -148,16 +172,45 @@ def ptr(t):
 
 
 def require_cuda(*tensors):
+    """All tensors must live on ONE CUDA device; returns that device."""
+    dev = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError(
                 "the PFN hot path runs on sm_100a CUDA kernels only; got a tensor on "
                 f"{t.device}. Move the model and data to a CUDA device (no CPU fallback exists).")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"tensors of one kernel call live on different devices ({dev} and {t.device})")
+    return dev
+
+
+def _guarded(fn):
+    """Run the wrapped library call with the device of its first tensor argument as the current device (so that
+    `stream_ptr()`, `num_sms()` and the launch itself all refer to the device that owns the data)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = None
+        for a in args:
+            if torch.is_tensor(a) and a.is_cuda:
+                dev = a.device
+                break
+        if dev is None:
+            return fn(*args, **kwargs)
+        with on_device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
 
 
 # ------------------------------------------------------------------------------------------------
 # thin wrappers
 # ------------------------------------------------------------------------------------------------
+@_guarded
 def gemm(A, B, C, *, a_mn_major=False, b_mn_major=False, bias=None, aux=None, C2=None, epilogue=EPI_NONE,
          accumulate=False, k_splits=1, M=None, N=None, K=None, use_tc=None):
     """C[M,N] (+)= epi(A . B^T-ish + bias) (+ aux).  Operands are 2-D row-major tensors (stride(1) == 1)."""
@@ -227,6 +280,7 @@ def tc_attention_ok(qkv, dh, T=None):
     return qkv.dtype == torch.bfloat16 and dh == 128 and qkv.stride(0) % 8 == 0 and qkv.data_ptr() % 16 == 0
 
 
+@_guarded
 def attention_fwd(qkv, out, lse, T, B, H, dh, sep, use_tc=None, batch_major=False):
     _count(1)
     lib = load()
@@ -238,6 +292,7 @@ def attention_fwd(qkv, out, lse, T, B, H, dh, sep, use_tc=None, batch_major=Fals
     check(fn(ctypes.byref(d), stream_ptr()), "pfn_attention_fwd")
 
 
+@_guarded
 def attention_bwd(qkv, out, lse, dout, dqkv, delta, T, B, H, dh, sep, use_tc=None, batch_major=False):
     _count(2)
     lib = load()
@@ -249,6 +304,7 @@ def attention_bwd(qkv, out, lse, dout, dqkv, delta, T, B, H, dh, sep, use_tc=Non
     check(fn(ctypes.byref(d), stream_ptr()), "pfn_attention_bwd")
 
 
+@_guarded
 def embed_fwd(x, y, Wx, bx, wy, by, out, T, B, F, E, sep):
     _count(1)
     require_cuda(x, y, Wx, bx, wy, by, out)
@@ -256,6 +312,7 @@ def embed_fwd(x, y, Wx, bx, wy, by, out, T, B, F, E, sep):
                                E, sep, stream_ptr()), "pfn_embed_fwd")
 
 
+@_guarded
 def embed_bwd(dout, x, y, dWx, dbx, dwy, dby, T, B, F, E, sep):
     _count((F + 7) // 8)
     require_cuda(dout, x, y, dWx, dbx, dwy, dby)
@@ -263,6 +320,7 @@ def embed_bwd(dout, x, y, dWx, dbx, dwy, dby, T, B, F, E, sep):
                                B, F, E, sep, stream_ptr()), "pfn_embed_bwd")
 
 
+@_guarded
 def layernorm_fwd(z, gamma, beta, h, mean, rstd, eps=1e-5):
     _count(1)
     require_cuda(z, gamma, beta, h, mean, rstd)
@@ -271,6 +329,7 @@ def layernorm_fwd(z, gamma, beta, h, mean, rstd, eps=1e-5):
                                    ptr(rstd), rows, E, eps, dtype_code(z), stream_ptr()), "pfn_layernorm_fwd")
 
 
+@_guarded
 def layernorm_bwd(dh, z, mean, rstd, gamma, dz, dgamma, dbeta, colsum_out=None):
     _count(1)
     require_cuda(dh, z, mean, rstd, gamma, dz, dgamma, dbeta, colsum_out)
@@ -280,6 +339,7 @@ def layernorm_bwd(dh, z, mean, rstd, gamma, dz, dgamma, dbeta, colsum_out=None):
                                    dtype_code(z), stream_ptr()), "pfn_layernorm_bwd")
 
 
+@_guarded
 def colsum(X, out, N=None):
     _count(1)
     require_cuda(X, out)
@@ -288,6 +348,7 @@ def colsum(X, out, N=None):
     check(load().pfn_colsum(ptr(X), X.stride(0), dtype_code(X), ptr(out), rows, N, stream_ptr()), "pfn_colsum")
 
 
+@_guarded
 def bar_nll_fwd(logits, y, borders, n_bars, full_support, nll, idx, lse, oob_count):
     _count(1)
     require_cuda(logits, y, borders, nll, idx, lse, oob_count)
@@ -297,6 +358,7 @@ def bar_nll_fwd(logits, y, borders, n_bars, full_support, nll, idx, lse, oob_cou
           "pfn_bar_nll_fwd")
 
 
+@_guarded
 def bar_nll_bwd(logits, idx, lse, g, dlogits, n_bars, n_cols_pad=None):
     _count(1)
     require_cuda(logits, idx, lse, g, dlogits)
@@ -307,6 +369,7 @@ def bar_nll_bwd(logits, idx, lse, g, dlogits, n_bars, n_cols_pad=None):
                                  stream_ptr()), "pfn_bar_nll_bwd")
 
 
+@_guarded
 def bar_bucket_idx(y, borders, n_bars, idx):
     _count(1)
     require_cuda(y, borders, idx)
@@ -314,6 +377,7 @@ def bar_bucket_idx(y, borders, n_bars, idx):
           "pfn_bar_bucket_idx")
 
 
+@_guarded
 def gp_sample(x, z, ls, os_, noise, jitter, kernel_type, y, work, info):
     _count(1)
     require_cuda(x, z, ls, os_, noise, y, work, info)

@@ -255,11 +255,6 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
         tc::mbar_wait(qdo_empty, (tcount & 1) ^ 1);
         if (lane == 0) tr.log(1, tcount, 0);
         if (tc::elect_one()) {
-#ifdef PFN_DBG_DQ_NOQTMA
-          tc::mbar_arrive(qdo_full);
-        }
-        if (false) {
-#endif
           tc::mbar_expect_tx(qdo_full, 2 * AB_TILE_BYTES);
           tc::tma_load_3d(sQ, &tmQKV128, qdo_full, h * AB_DH, b, i0);
           tc::tma_load_3d(sQ + 16384, &tmQKV128, qdo_full, h * AB_DH + 64, b, i0);
@@ -275,11 +270,6 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
           uint8_t* vdst = kdst + AB_BLK_BYTES;
           const int j0 = j < nblk ? j * 64 : dstart[j - nblk];
           if (tc::elect_one()) {
-#ifdef PFN_DBG_DQ_NOKVTMA
-            tc::mbar_arrive(&kv_full[st]);
-          }
-          if (false) {
-#endif
             tc::mbar_expect_tx(&kv_full[st], 2 * AB_BLK_BYTES);
             tc::tma_load_3d(kdst, &tmQKV64, &kv_full[st], E + h * AB_DH, b, j0);
             tc::tma_load_3d(kdst + 8192, &tmQKV64, &kv_full[st], E + h * AB_DH + 64, b, j0);
@@ -299,10 +289,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
         const uint32_t k_addr = tc::smem_u32(sKV + (gg % AB_KS) * 2 * AB_BLK_BYTES);
         const uint32_t sb = gg % 3;
         if (tc::elect_one()) {
-#ifndef PFN_DBG_DQ_NOSCORES
           ab_mma_ss_128x64(tmem_base + sb * 64, q_addr, k_addr);                        // S  = Q K^T
           ab_mma_ss_128x64(tmem_base + 192 + sb * 64, do_addr, k_addr + AB_BLK_BYTES);  // dP = dO V^T
-#endif
           tc::umma_commit(&s_full[sb]);
         }
         __syncwarp();
@@ -348,9 +336,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
           kv_ok = (j + 3 < nb) ? tc::mbar_try_wait(&kv_full[(g + 3) % AB_KS], ((g + 3) / AB_KS) & 1) : false;
           const uint32_t k_addr = tc::smem_u32(sKV + (g % AB_KS) * 2 * AB_BLK_BYTES);
           if (tc::elect_one()) {
-#ifndef PFN_DBG_DQ_NOACC
             ab_mma_ts_128x128(tmem_base + 384, tmem_base + (g % 3) * 64, k_addr, j > 0);     // dQ += dS K
-#endif
             tc::umma_commit(&kv_empty[g % AB_KS]);
             if (j + 1 == nb) tc::umma_commit(dq_done);     // one phase per tile: the parity wait below is unambiguous
           }
@@ -393,12 +379,6 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
         tc::tmem_ld_32x32b_x32(tmem_base + lane_off + buf * 64 + half * 32, s);
         tc::tmem_ld_32x32b_x32(tmem_base + lane_off + 192 + buf * 64 + half * 32, dp);
         tc::tmem_ld_wait();
-#ifdef PFN_DBG_DQ_NOMATH
-        if (true) {
-#pragma unroll
-          for (int c = 0; c < 16; ++c) pk[c] = s[2 * c] ^ dp[2 * c + 1];
-        } else
-#endif
         if (dense && kmax >= 64) {
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
@@ -467,7 +447,6 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
       tc::tc_fence_after();
       const size_t tok = p.batch_major ? static_cast<size_t>(b) * p.T + (valid ? i : 0) : static_cast<size_t>(valid ? i : 0) * p.B + b;
       __nv_bfloat16* dq_out = p.dqkv + tok * p.ld_dqkv + h * AB_DH;
-#ifndef PFN_DBG_DQ_NOEPI
 #pragma unroll 1
       for (int cc = 0; cc < 2; ++cc) {
         const int c = half * 2 + cc;                      // the pair splits the four 32-column chunks
@@ -479,344 +458,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
         for (int e = 0; e < 32; ++e) acc[e] = __uint_as_float(raw[e]);
         if (valid) ab_store32(dq_out + c * 32, acc);
       }
-#endif
       tc::tc_fence_before();
       tc::mbar_arrive_warp(dq_empty);
       if (lane == 0) tr.log(23 + 100 * warp, tcount, 0);
-    }
-  }
-
-  tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc::tc_fence_after();
-    tc::tmem_dealloc(tmem_base, 512);
-  }
-}
-
-// =====================================================================================================================
-// Kernel 1b: dQ for a PAIR of query tiles of the same (batch, head) -- two independent hand-off chains on one SM
-// =====================================================================================================================
-// EXPERIMENT (round 1, off by default: PFN_ATTN_DQ_PAIR=1): measured 1.81 ms vs 1.52 ms for the single-tile kernel -- with a
-// whole 64-key row per thread the exp/convert stage of a tile takes twice as long and the two chains did not overlap enough.
-// The single-tile kernel above is a serial chain (tools/ab_attn.py ablations: score MMAs -> row threads -> accumulate MMA
-// add up almost linearly; the MMAs themselves are 0.13 of its 1.52 ms).  Here one CTA owns TWO 128-row tiles (A, B):
-// they share every dense 64-key K/V block in shared memory (K/V TMA traffic halves), warps 2..5 serve tile A and warps
-// 6..9 tile B (one thread per row, all 64 columns of a block), and the MMA warp alternates A and B, so one tile's
-// exp/convert work and barrier round trips run under the other tile's MMAs.
-//   smem : Q_A,dO_A | Q_B,dO_B (2 x 64 KB) | 3-stage K/V block ring (3 x 32 KB)
-//   TMEM : tile X at column X*256: S @+0 (64, overwritten in place by packed bf16 dS) | dP @+64 | dQ @+128
-//   ring : dense blocks 0..nblk-1 (both tiles), then A's diagonal blocks, then B's diagonal blocks
-// ring position of block k of tile x (0 = A, 1 = B) inside a pair: dense blocks are shared, diagonal blocks follow in the
-// order the MMA warp consumes them: (A, k), (B, k) for k = nblk, nblk + 1
-__device__ __forceinline__ int ab2_ring_of(int nblk, int nba, int nbb, int x, int k) {
-  if (k < nblk) return k;
-  int r = nblk;
-  for (int kk = nblk; kk < k; ++kk) r += (kk < nba ? 1 : 0) + (kk < nbb ? 1 : 0);
-  if (x == 1 && k < nba) r += 1;
-  return r;
-}
-
-constexpr int AB2_KS = 3;
-constexpr int AB2_SMEM = 4 * AB_TILE_BYTES + AB2_KS * 2 * AB_BLK_BYTES + 256 + 1024;
-
-__global__ void __launch_bounds__(AB_THREADS, 1)
-attn_bwd_dq2_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
-                       const __grid_constant__ CUtensorMap tmDO128, const AttnBwdParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQD = smem;                                         // tile X: Q at X*64K, dO at X*64K + 32K
-  uint8_t* sKV = smem + 4 * AB_TILE_BYTES;                     // stage s: K at +s*32K, V at +16K
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 4 * AB_TILE_BYTES + AB2_KS * 2 * AB_BLK_BYTES);
-  uint64_t* qdo_full = bars + 0;
-  uint64_t* qdo_empty = bars + 1;                  // MMA commit after the pair's last score MMA + all 8 row warps
-  uint64_t* kv_full = bars + 2;                    // [AB2_KS]
-  uint64_t* kv_empty = kv_full + AB2_KS;           // [AB2_KS]
-  uint64_t* s_full = kv_empty + AB2_KS;            // [2] per tile: one phase per block of that tile
-  uint64_t* ds_ready = s_full + 2;                 // [2] four warps each
-  uint64_t* dq_done = ds_ready + 2;                // [2] one phase per pair
-  uint64_t* dq_empty = dq_done + 2;                // [2] four warps each
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_empty + 2);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int E = p.H * AB_DH;
-
-  if (warp == 0 && lane == 0) {
-    tc::tma_prefetch_desc(&tmQKV128);
-    tc::tma_prefetch_desc(&tmQKV64);
-    tc::tma_prefetch_desc(&tmDO128);
-  }
-  if (warp == 1 && lane == 0) {
-    tc::mbar_init(qdo_full, 1);
-    tc::mbar_init(qdo_empty, 1 + AB_EW_WARPS);
-    for (int s = 0; s < AB2_KS; ++s) {
-      tc::mbar_init(&kv_full[s], 1);
-      tc::mbar_init(&kv_empty[s], 1);
-    }
-    for (int x = 0; x < 2; ++x) {
-      tc::mbar_init(&s_full[x], 1);
-      tc::mbar_init(&ds_ready[x], AB_EW_WARPS / 2);
-      tc::mbar_init(&dq_done[x], 1);
-      tc::mbar_init(&dq_empty[x], AB_EW_WARPS / 2);
-    }
-    tc::mbar_fence_init();
-  }
-  if (warp == 2) {
-    tc::tmem_alloc(tmem_slot, 512);
-    tc::tmem_relinquish();
-  }
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const int nblk = (p.sep + 63) / 64;
-  const int n_pairs = (p.n_tiles + 1) / 2;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------------------------------------------ TMA producer
-    uint32_t r = 0, pcount = 0;                       // running ring-block counter, pair counter
-    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++pcount) {
-      const int bh = w / n_pairs;
-      const int tp = w - bh * n_pairs;
-      const int b = bh / p.H, h = bh - b * p.H;
-      const int ia = tp * 256, ib = ia + 128;
-      const bool has_b = ib < p.T;
-      int dsa[2], dsb[2] = {0, 0};
-      const int nba = ab_tile_block_plan(ia, p.sep, p.T, nblk, dsa);
-      const int nbb = has_b ? ab_tile_block_plan(ib, p.sep, p.T, nblk, dsb) : 0;
-      const int ring_blocks = nba + (has_b ? nbb - nblk : 0);
-      tc::mbar_wait(qdo_empty, (pcount & 1) ^ 1);
-      if (tc::elect_one()) {
-        tc::mbar_expect_tx(qdo_full, (has_b ? 4 : 2) * AB_TILE_BYTES);
-        for (int x = 0; x < (has_b ? 2 : 1); ++x) {
-          uint8_t* q = sQD + x * 2 * AB_TILE_BYTES;
-          const int i0 = ia + x * 128;
-          tc::tma_load_3d(q, &tmQKV128, qdo_full, h * AB_DH, b, i0);
-          tc::tma_load_3d(q + 16384, &tmQKV128, qdo_full, h * AB_DH + 64, b, i0);
-          tc::tma_load_3d(q + AB_TILE_BYTES, &tmDO128, qdo_full, h * AB_DH, b, i0);
-          tc::tma_load_3d(q + AB_TILE_BYTES + 16384, &tmDO128, qdo_full, h * AB_DH + 64, b, i0);
-        }
-      }
-      __syncwarp();
-      // key offset of every ring block, in ring order
-      int j0s[4] = {0, 0, 0, 0};
-      for (int k = nblk; k < nblk + 2; ++k) {
-        if (k < nba) j0s[ab2_ring_of(nblk, nba, nbb, 0, k) - nblk] = dsa[k - nblk];
-        if (k < nbb) j0s[ab2_ring_of(nblk, nba, nbb, 1, k) - nblk] = dsb[k - nblk];
-      }
-      for (int j = 0; j < ring_blocks; ++j, ++r) {
-        const int st = r % AB2_KS;
-        tc::mbar_wait(&kv_empty[st], ((r / AB2_KS) & 1) ^ 1);
-        uint8_t* kdst = sKV + st * 2 * AB_BLK_BYTES;
-        uint8_t* vdst = kdst + AB_BLK_BYTES;
-        int j0 = j * 64;
-        if (j >= nblk) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) j0 = (j - nblk == q) ? j0s[q] : j0;
-        }
-        if (tc::elect_one()) {
-          tc::mbar_expect_tx(&kv_full[st], 2 * AB_BLK_BYTES);
-          tc::tma_load_3d(kdst, &tmQKV64, &kv_full[st], E + h * AB_DH, b, j0);
-          tc::tma_load_3d(kdst + 8192, &tmQKV64, &kv_full[st], E + h * AB_DH + 64, b, j0);
-          tc::tma_load_3d(vdst, &tmQKV64, &kv_full[st], 2 * E + h * AB_DH, b, j0);
-          tc::tma_load_3d(vdst + 8192, &tmQKV64, &kv_full[st], 2 * E + h * AB_DH + 64, b, j0);
-        }
-        __syncwarp();
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------------------------------------ MMA issuer
-    uint32_t r0 = 0, pcount = 0;                      // ring counter at the start of the pair
-    uint32_t nsc[2] = {0, 0};                         // blocks scored so far per tile (running over all pairs): s_full phase
-    uint32_t nact[2] = {0, 0};                        // pairs so far in which the tile slot was active: dq_done / dq_empty phase
-    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++pcount) {
-      const int bh = w / n_pairs;
-      const int tp = w - bh * n_pairs;
-      const int ia = tp * 256, ib = ia + 128;
-      const bool has_b = ib < p.T;
-      int dsa[2], dsb[2] = {0, 0};
-      const int nba = ab_tile_block_plan(ia, p.sep, p.T, nblk, dsa);
-      const int nbb = has_b ? ab_tile_block_plan(ib, p.sep, p.T, nblk, dsb) : 0;
-      const int nbx[2] = {nba, nbb};
-      int sc[2] = {0, 0}, ac[2] = {0, 0};             // per tile: next block to score / to accumulate (index in the tile's list)
-      int scores_left = nba + nbb;
-      tc::mbar_wait(qdo_full, pcount & 1);
-      tc::tc_fence_after();
-      // ring index of block k of tile x:  dense k < nblk -> k ; A diag -> k ; B diag -> nba + (k - nblk)
-      auto ring_of = [&](int x, int k) { return ab2_ring_of(nblk, nba, nbb, x, k); };
-      // the last user of a ring block frees its stage: dense blocks are shared (B accumulates after A), diagonal blocks are private
-      auto frees_stage = [&](int x, int k) { return (k >= nblk) || x == 1 || !has_b; };
-      auto step_scores = [&](int x) {
-        if (sc[x] >= nbx[x]) return;
-        const int k = sc[x]++;
-        const uint32_t rr = r0 + ring_of(x, k);
-        const uint32_t st = rr % AB2_KS;
-        tc::mbar_wait(&kv_full[st], (rr / AB2_KS) & 1);
-        tc::tc_fence_after();
-        const uint32_t q_addr = tc::smem_u32(sQD + x * 2 * AB_TILE_BYTES);
-        const uint32_t k_addr = tc::smem_u32(sKV + st * 2 * AB_BLK_BYTES);
-        const uint32_t tb = tmem_base + x * 256;
-        --scores_left;
-        if (tc::elect_one()) {
-          ab_mma_ss_128x64(tb, q_addr, k_addr);                                        // S  = Q K^T
-          ab_mma_ss_128x64(tb + 64, q_addr + AB_TILE_BYTES, k_addr + AB_BLK_BYTES);   // dP = dO V^T
-          tc::umma_commit(&s_full[x]);
-          if (scores_left == 0) tc::umma_commit(qdo_empty);                            // every score MMA of the pair is issued
-        }
-        __syncwarp();
-        ++nsc[x];
-      };
-      auto step_acc = [&](int x) {
-        if (ac[x] >= nbx[x]) return;
-        const int k = ac[x]++;
-        const uint32_t rr = r0 + ring_of(x, k);
-        const uint32_t st = rr % AB2_KS;
-        // ds_ready[x]: one phase per block of tile x; this is block number (nsc[x] - 1) of the tile's running count
-        tc::mbar_wait(&ds_ready[x], (nsc[x] - 1) & 1);
-        if (k == 0) tc::mbar_wait(&dq_empty[x], (nact[x] & 1) ^ 1);
-        tc::tc_fence_after();
-        const uint32_t k_addr = tc::smem_u32(sKV + st * 2 * AB_BLK_BYTES);
-        const uint32_t tb = tmem_base + x * 256;
-        if (tc::elect_one()) {
-          ab_mma_ts_128x128(tb + 128, tb, k_addr, k > 0);                              // dQ += dS K
-          if (frees_stage(x, k)) tc::umma_commit(&kv_empty[st]);
-          if (k + 1 == nbx[x]) tc::umma_commit(&dq_done[x]);
-        }
-        __syncwarp();
-      };
-      step_scores(0);
-      step_scores(1);
-      while (ac[0] < nbx[0] || ac[1] < nbx[1]) {
-        step_acc(0);
-        step_scores(0);       // the S / dP columns of tile A are free again: dQ_A of the previous block is issued (in-order pipe)
-        step_acc(1);
-        step_scores(1);
-      }
-      r0 += nba + (has_b ? nbb - nblk : 0);
-      ++nact[0];
-      if (has_b) ++nact[1];
-    }
-  } else {
-    // ------------------------------------------------------------------------------------------------ row threads
-    const int quarter = warp & 3;                 // TMEM lane quarter this warp may touch
-    const int x = (warp - 2) >> 2;                // tile served by this warp group
-    const int row = quarter * 32 + lane;
-    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t tb = tmem_base + x * 256 + lane_off;
-    const uint8_t* sQ = sQD + x * 2 * AB_TILE_BYTES;
-    const uint8_t* sDO = sQ + AB_TILE_BYTES;
-    uint32_t nblocks = 0, pcount = 0, nact = 0;   // running block count of this tile slot (s_full / ds_ready phases); active pairs
-    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++pcount) {
-      const int bh = w / n_pairs;
-      const int tp = w - bh * n_pairs;
-      const int b = bh / p.H, h = bh - b * p.H;
-      const int i0 = tp * 256 + x * 128;
-      const bool active = i0 < p.T;
-      const int i = i0 + row;
-      const bool valid = i < p.T;
-      const bool is_query = valid && i >= p.sep;
-      int dstart[2] = {0, 0};
-      const int nb = active ? ab_tile_block_plan(i0, p.sep, p.T, nblk, dstart) : 0;
-      tc::mbar_wait(qdo_full, pcount & 1);     // acquire the TMA-written Q / dO tiles (rows are read back in diagonal blocks)
-      float lse2 = INFINITY, dls = 0.f;       // dls = delta * scale
-      if (valid) {
-        lse2 = p.lse[static_cast<size_t>(bh) * p.T + i] * 1.4426950408889634f;
-        dls = p.delta[static_cast<size_t>(bh) * p.T + i] * p.scale;
-      }
-      for (int j = 0; j < nb; ++j, ++nblocks) {
-        tc::mbar_wait(&s_full[x], nblocks & 1);
-        tc::tc_fence_after();
-        const bool dense = j < nblk;
-        const int kmax = dense ? p.sep - j * 64 : 0;
-        int cl_row = -1;                                  // own (diagonal) column of this row inside the block, if any
-        if (!dense) {
-          const int c = i - dstart[j - nblk];
-          if (is_query && c >= 0 && c < 64) cl_row = c;
-        }
-#pragma unroll 1
-        for (int hh = 0; hh < 2; ++hh) {                  // the two 32-column halves of the row
-          uint32_t s[32], dp[32], pk[16];
-          tc::tmem_ld_32x32b_x32(tb + hh * 32, s);
-          tc::tmem_ld_32x32b_x32(tb + 64 + hh * 32, dp);
-          tc::tmem_ld_wait();
-          if (dense && kmax >= 64) {
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-              const float p0 = tc::fast_exp2(fmaf(__uint_as_float(s[2 * c]), p.scale_log2, -lse2));
-              const float p1 = tc::fast_exp2(fmaf(__uint_as_float(s[2 * c + 1]), p.scale_log2, -lse2));
-              pk[c] = tc::pack_bf16x2(p0 * fmaf(__uint_as_float(dp[2 * c]), p.scale, -dls),
-                                      p1 * fmaf(__uint_as_float(dp[2 * c + 1]), p.scale, -dls));
-            }
-          } else if (dense) {
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-              const int k0 = hh * 32 + 2 * c;
-              float d0 = 0.f, d1 = 0.f;
-              if (k0 < kmax)
-                d0 = tc::fast_exp2(fmaf(__uint_as_float(s[2 * c]), p.scale_log2, -lse2)) * fmaf(__uint_as_float(dp[2 * c]), p.scale, -dls);
-              if (k0 + 1 < kmax)
-                d1 = tc::fast_exp2(fmaf(__uint_as_float(s[2 * c + 1]), p.scale_log2, -lse2)) * fmaf(__uint_as_float(dp[2 * c + 1]), p.scale, -dls);
-              pk[c] = tc::pack_bf16x2(d0, d1);
-            }
-          } else {
-            const int cl = (cl_row >= hh * 32 && cl_row < hh * 32 + 32) ? cl_row - hh * 32 : -1;
-            float sv = 0.f, dv = 0.f;
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              sv = (c == cl) ? __uint_as_float(s[c]) : sv;
-              dv = (c == cl) ? __uint_as_float(dp[c]) : dv;
-            }
-            float dself = 0.f;
-            if (cl >= 0) {
-              // the diagonal key is attended by this row only: dK_i = dS_ii q_i and dV_i = P_ii dO_i are complete.
-              const float pii = tc::fast_exp2(fmaf(sv, p.scale_log2, -lse2));
-              dself = pii * fmaf(dv, p.scale, -dls);
-              const size_t tokq = p.batch_major ? static_cast<size_t>(b) * p.T + i : static_cast<size_t>(i) * p.B + b;
-              __nv_bfloat16* dkv_out = p.dqkv + tokq * p.ld_dqkv + h * AB_DH;
-#pragma unroll 1
-              for (int c = 0; c < 4; ++c) {
-                float qq[32], dd[32];
-                ab_load32_swz(sQ, row, c * 32, qq);
-                ab_load32_swz(sDO, row, c * 32, dd);
-#pragma unroll
-                for (int e = 0; e < 32; ++e) { qq[e] *= dself; dd[e] *= pii; }
-                ab_store32(dkv_out + E + c * 32, qq);
-                ab_store32(dkv_out + 2 * E + c * 32, dd);
-              }
-            }
-            const uint32_t lo = tc::pack_bf16x2(dself, 0.f), hi = tc::pack_bf16x2(0.f, dself);
-            const int cw = cl >> 1;                         // -1 >> 1 == -1: matches nothing
-            const uint32_t word = (cl & 1) ? hi : lo;
-#pragma unroll
-            for (int c = 0; c < 16; ++c) pk[c] = (c == cw) ? word : 0u;
-          }
-          tc::tmem_st_32x32b_x16(tb + hh * 16, pk);
-        }
-        tc::tmem_st_wait();
-        tc::tc_fence_before();
-        tc::mbar_arrive_warp(&ds_ready[x]);
-      }
-      tc::mbar_arrive_warp(qdo_empty);                        // this warp no longer reads the Q / dO tiles
-      if (active) {
-        tc::mbar_wait(&dq_done[x], nact & 1);                 // committed once per active pair, after the tile's last dQ MMA
-        tc::tc_fence_after();
-        const size_t tok = p.batch_major ? static_cast<size_t>(b) * p.T + (valid ? i : 0) : static_cast<size_t>(valid ? i : 0) * p.B + b;
-        __nv_bfloat16* dq_out = p.dqkv + tok * p.ld_dqkv + h * AB_DH;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t raw[32];
-          float acc[32];
-          tc::tmem_ld_32x32b_x32(tb + 128 + c * 32, raw);
-          tc::tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 32; ++e) acc[e] = __uint_as_float(raw[e]);
-          if (valid) ab_store32(dq_out + c * 32, acc);
-        }
-        tc::tc_fence_before();
-        tc::mbar_arrive_warp(&dq_empty[x]);
-        ++nact;
-      }
     }
   }
 
@@ -1120,12 +764,10 @@ extern "C" int pfn_attention_bwd_tc(const pfn_attn_desc* d, void* stream) {
   p.lse = d->lse; p.delta = d->delta;
   p.batch_major = d->batch_major;
   p.trace = nullptr; p.trace_cap = g_trace_cap;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (first_use_on_device(attr_set)) {
     PFN_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
     PFN_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
-    PFN_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB2_SMEM));
-    attr_set = true;
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   // debug only (tools/time_kernels.py): pfn_debug_attention_trace(NULL, 0, 21|22|23) runs just dK/dV | dQ | delta
@@ -1138,20 +780,12 @@ extern "C" int pfn_attention_bwd_tc(const pfn_attn_desc* d, void* stream) {
     PFN_LAUNCH_OK();
   }
   if (only == 0 || only == 22) {
-    // experimental tile-pair variant (correct, parity-tested, but measured slower: 1.81 vs 1.52 ms at cfg 2): opt-in only
-    static const bool pair_kernel = []() { const char* e = getenv("PFN_ATTN_DQ_PAIR"); return e && e[0] == '1'; }();
     p.n_tiles = (d->T + 127) / 128;
-    if (pair_kernel && g_trace_which != 1) {
-      p.total_work = ((p.n_tiles + 1) / 2) * d->B * d->H;
-      int grid = num_sms() < p.total_work ? num_sms() : p.total_work;
-      attn_bwd_dq2_tc_kernel<<<grid, AB_THREADS, AB2_SMEM, s>>>(tmQKV128, tmQKV64, tmDO128, p);
-    } else {
-      p.total_work = p.n_tiles * d->B * d->H;
-      int grid = num_sms() < p.total_work ? num_sms() : p.total_work;
-      p.trace = g_trace_which == 1 ? g_trace_ptr : nullptr;
-      attn_bwd_dq_tc_kernel<<<grid, AB_THREADS, AB_SMEM, s>>>(tmQKV128, tmQKV64, tmDO128, p);
-      p.trace = nullptr;
-    }
+    p.total_work = p.n_tiles * d->B * d->H;
+    int grid = num_sms() < p.total_work ? num_sms() : p.total_work;
+    p.trace = g_trace_which == 1 ? g_trace_ptr : nullptr;
+    attn_bwd_dq_tc_kernel<<<grid, AB_THREADS, AB_SMEM, s>>>(tmQKV128, tmQKV64, tmDO128, p);
+    p.trace = nullptr;
     PFN_LAUNCH_OK();
   }
   if (d->sep > 0 && (only == 0 || only == 21)) {

@@ -456,11 +456,10 @@ extern "C" int pfn_attention_fwd_tc(const pfn_attn_desc* d, void* stream) {
   p.batch_major = d->batch_major;
   p.trace = g_trace_which == 0 ? g_trace_ptr : nullptr;
   p.trace_cap = g_trace_cap;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (first_use_on_device(attr_set)) {
     PFN_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWD_SMEM));
     PFN_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    attr_set = true;
   }
   int grid = 2 * num_sms();
   if (grid > p.total_work) grid = p.total_work;

@@ -146,4 +146,13 @@ __device__ __forceinline__ float gelu_grad_fast(float u) {
 
 int num_sms();
 
+// Per-device one-time setup guard (function attributes such as the dynamic shared-memory limit are per device).
+inline bool first_use_on_device(bool (&done)[64]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  if (done[dev]) return false;
+  done[dev] = true;
+  return true;
+}
+
 }  // namespace pfn

@@ -607,10 +607,9 @@ static int launch_gemm_tc(const pfn_gemm_desc* d, cudaStream_t stream) {
   PFN_CHECK_ARG(!p.accumulate || p.c_f32, "gemm_tc: accumulate / split-K requires an fp32 output");
   const int total = p.tiles_m * p.tiles_n * splits;
   auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN, CTA2>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (first_use_on_device(attr_set)) {
     PFN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
   }
   if constexpr (!CTA2) {
     const int grid = total < num_sms() ? total : num_sms();

@@ -249,10 +249,9 @@ extern "C" int pfn_gp_sample(const float* x, const float* z, const float* ls, co
   PFN_CHECK_ARG((reinterpret_cast<uintptr_t>(work) & 15) == 0, "gp_sample: work buffer must be 16-byte aligned");
   const int ldw = (T + 3) & ~3;
   constexpr int kDynSmem = GP_STAGES * (NB * TR + NB * NB) * static_cast<int>(sizeof(float));
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (first_use_on_device(attr_set)) {
     PFN_CUDA_OK(cudaFuncSetAttribute(gp_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem));
-    attr_set = true;
   }
   gp_sample_kernel<<<Bn, 256, kDynSmem, reinterpret_cast<cudaStream_t>(stream)>>>(x, z, ls, os, noise, jitter, kernel_type, y,
                                                                          work, info, T, F, ldw);

@@ -84,14 +84,16 @@ class EncoderStackFn(torch.autograd.Function):
     """src [T*B, E] (activation dtype) -> output of `nlayers` post-norm encoder layers under the sep mask."""
 
     @staticmethod
-    def forward(ctx, src, T, B, sep, nhead, precision, *params):
+    def forward(ctx, src, T, B, sep, nhead, precision, keep, *params):
+        """`keep`: the CALLER's grad mode (torch.is_grad_enabled() outside this Function — inside it is always off, and
+        ctx.needs_input_grad does not reflect no_grad); when False no activation is retained (inference memory)."""
         L.require_cuda(src, *params)
         dt = act_dtype(precision)
         assert src.dtype == dt and src.dim() == 2
         n_layers = len(params) // N_LAYER_PARAMS
         N, E = src.shape
         dh = E // nhead
-        keep = any(ctx.needs_input_grad)   # grad mode is off inside Function.forward; this reflects the caller's mode
+        keep = bool(keep) and any(ctx.needs_input_grad)
         saved = []
         h = src.contiguous()
         for li in range(n_layers):
@@ -122,6 +124,9 @@ class EncoderStackFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
+        if ctx.saved_acts is None:
+            raise RuntimeError("EncoderStackFn: activations were already released by a previous backward "
+                               "(the engine frees them layer by layer; retain_graph=True is not supported)")
         T, B, sep, nhead, precision, n_layers = ctx.meta
         dt = act_dtype(precision)
         params = ctx.params
@@ -167,7 +172,7 @@ class EncoderStackFn(torch.autograd.Function):
             dh2 = _linear_dgrad(dqkv, in_w, aux=dz1)
             del dqkv, dz1, h
         ctx.saved_acts = None
-        return (dh2, None, None, None, None, None) + tuple(grads)
+        return (dh2, None, None, None, None, None, None) + tuple(grads)
 
 
 class EmbedFn(torch.autograd.Function):

@@ -14,7 +14,7 @@ import torch
 
 from .. import _lib as L
 from ..utils import default_device
-from .utils import get_batch_to_dataloader
+from .utils import get_batch_to_dataloader, _Deferred
 
 _JITTERS = (0.0, 1e-6, 1e-5, 1e-4)
 
@@ -41,10 +41,44 @@ def sample_gp(x, z, lengthscale, outputscale, noise, kernel_type=L.KERNEL_RBF, r
     y = torch.empty(Bn, T, device=dev, dtype=torch.float32)
     work = torch.empty(Bn, T, ldw, device=dev, dtype=torch.float32)
     info = torch.empty(Bn, device=dev, dtype=torch.int32)
-    for jitter in _JITTERS:
-        L.gp_sample(x, z, lengthscale, outputscale, noise, jitter, kernel_type, y, work, info)
-        if not bool(info.any().item()):
-            return (y, torch.tril(work[:, :, :T].transpose(1, 2))) if return_factor else y
+
+    def attempt(jitters):
+        for jitter in jitters:
+            L.gp_sample(x, z, lengthscale, outputscale, noise, jitter, kernel_type, y, work, info)
+            if not bool(info.any().item()):
+                return
+        raise NotPSDError(f"kernel matrix not positive definite even with jitter {_JITTERS[-1]:g} "
+                          f"(first failing pivots: {info[info > 0][:8].tolist()})")
+
+    if _Deferred.active and not return_factor:
+        # No host sync here: the pivot flags travel to pinned host memory behind the kernel and are looked at when the
+        # batch is handed to the consumer (a step later).  Only then -- and only if a pivot failed -- is the whole batch
+        # re-factored with gpytorch's jitter escalation, overwriting y in place (every view handed out stays valid).
+        L.gp_sample(x, z, lengthscale, outputscale, noise, _JITTERS[0], kernel_type, y, work, info)
+        bad = info.max().reshape(1)
+        bad_host = torch.empty(1, dtype=torch.int32, pin_memory=True)
+        bad_host.copy_(bad, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        del work
+
+        def resolve():
+            ev.synchronize()
+            if int(bad_host[0]) != 0:
+                nonlocal_work = torch.empty(Bn, T, ldw, device=dev, dtype=torch.float32)
+                _retry(x, z, lengthscale, outputscale, noise, kernel_type, y, nonlocal_work, info)
+        _Deferred.pending.append(resolve)
+        return y
+    attempt(_JITTERS)
+    return (y, torch.tril(work[:, :, :T].transpose(1, 2))) if return_factor else y
+
+
+def _retry(x, z, lengthscale, outputscale, noise, kernel_type, y, work, info):
+    with torch.cuda.device(x.device):
+        for jitter in _JITTERS[1:]:
+            L.gp_sample(x, z, lengthscale, outputscale, noise, jitter, kernel_type, y, work, info)
+            if not bool(info.any().item()):
+                return
     raise NotPSDError(f"kernel matrix not positive definite even with jitter {_JITTERS[-1]:g} "
                       f"(first failing pivots: {info[info > 0][:8].tolist()})")
 
@@ -58,16 +92,28 @@ def _hps_to_dict(hyperparameters):
 
 
 @torch.no_grad()
-def get_batch(batch_size, seq_len, num_features, device=default_device, hyperparameters=None, equidistant_x=False):
-    """-> x [T,B,F], y [T,B], target_y [T,B] (= y) on `device` (reference :36-58)."""
+def get_batch(batch_size, seq_len, num_features, device=default_device, hyperparameters=None, equidistant_x=False,
+              x=None, z=None):
+    """-> x [T,B,F], y [T,B], target_y [T,B] (= y) on `device` (reference :36-58).
+
+    Extension (defaults keep the reference signature): `x` [B,T,F] ~ U[0,1) and `z` [B,T] ~ N(0,1) may be supplied by
+    the caller — e.g. drawn on the host and kept in pinned memory — instead of being drawn on the device; they are
+    copied to the device asynchronously."""
     hps = _hps_to_dict(hyperparameters)
     dev = _compute_device(device)
-    if equidistant_x:
+    if x is not None:
+        assert x.shape == (batch_size, seq_len, num_features)
+        x = x.to(dev, torch.float32, non_blocking=True).contiguous()
+    elif equidistant_x:
         assert num_features == 1
         x = torch.linspace(0, 1., seq_len, device=dev).view(1, seq_len, 1).repeat(batch_size, 1, 1)
     else:
         x = torch.rand(batch_size, seq_len, num_features, device=dev)
-    z = torch.randn(batch_size, seq_len, device=dev)
+    if z is not None:
+        assert z.shape == (batch_size, seq_len)
+        z = z.to(dev, torch.float32, non_blocking=True).contiguous()
+    else:
+        z = torch.randn(batch_size, seq_len, device=dev)
     ls = torch.full((batch_size, num_features), float(hps["lengthscale"]), device=dev)
     os_ = torch.full((batch_size,), float(hps["outputscale"]), device=dev)
     noise = torch.full((batch_size,), float(hps["noise"]), device=dev)

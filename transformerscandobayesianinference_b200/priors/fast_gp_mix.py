@@ -16,7 +16,7 @@ from .. import _lib as L
 from ..bar_distribution import BarDistribution
 from ..utils import default_device
 from .fast_gp import _compute_device, sample_gp
-from .utils import get_batch_to_dataloader
+from .utils import get_batch_to_dataloader, _Deferred
 
 MIN_INFERRED_NOISE_LEVEL = 1e-4  # botorch.models.gp_regression.MIN_INFERRED_NOISE_LEVEL (noise constraint lower bound)
 
@@ -36,8 +36,9 @@ def sample_hyperparameters(n, num_features, hyperparameters, device):
 
 @torch.no_grad()
 def get_batch(batch_size, seq_len, num_features, device=default_device, hyperparameters=None,
-              batch_size_per_gp_sample=None, num_outputs=1, fix_to_range=None, equidistant_x=False):
-    """-> x [T,B,F], y [T,B], target_y [T,B] (reference :58-134)."""
+              batch_size_per_gp_sample=None, num_outputs=1, fix_to_range=None, equidistant_x=False, x=None, z=None):
+    """-> x [T,B,F], y [T,B], target_y [T,B] (reference :58-134).  `x` / `z`: optional caller-supplied uniform inputs
+    [B,T,F] and normal draws [B,T] (e.g. pinned host memory), see priors.fast_gp.get_batch; only without fix_to_range."""
     assert num_outputs == 1
     hps = hyperparameters or {}
     dev = _compute_device(device)
@@ -47,16 +48,33 @@ def get_batch(batch_size, seq_len, num_features, device=default_device, hyperpar
     mult = 2 ** (fix_to_range is not None)
     total = batch_size * mult
     cand = batch_size_per_gp_sample * mult
-    if equidistant_x:
+    given_z = None
+    if x is not None or z is not None:
+        assert fix_to_range is None, "caller-supplied x / z cannot be combined with the rejection loop of fix_to_range"
+    if z is not None:
+        given_z = z.to(dev, torch.float32, non_blocking=True).contiguous()
+    if x is not None:
+        assert x.shape == (total, seq_len, num_features)
+        x = x.to(dev, torch.float32, non_blocking=True).contiguous()
+    elif equidistant_x:
         assert num_features == 1
         x = torch.linspace(0, 1., seq_len, device=dev).view(1, seq_len, 1).repeat(total, 1, 1)
     else:
         x = torch.rand(total, seq_len, num_features, device=dev)
 
+    # post-processing reads y right away, so the deferred (sync-free) pivot check of sample_gp only applies to plain draws
+    plain = fix_to_range is None and not hps.get('y_minmax_norm') and not hps.get('sigmoid')
+
     def draw(xs):
+        if not plain and _Deferred.active:
+            _Deferred.active = False
+            try:
+                return draw(xs)
+            finally:
+                _Deferred.active = True
         n = xs.shape[0]
         ls, os_, noise = sample_hyperparameters(n, num_features, hps, dev)
-        z = torch.randn(n, seq_len, device=dev)
+        z = given_z if given_z is not None else torch.randn(n, seq_len, device=dev)
         s = sample_gp(xs.contiguous(), z, ls, os_, noise, kernel_type)   # [n, T]
         if hps.get('y_minmax_norm'):
             lo, hi = s.min(1, keepdim=True)[0], s.max(1, keepdim=True)[0]

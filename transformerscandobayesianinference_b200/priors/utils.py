@@ -11,6 +11,33 @@ from ..utils import set_locals_in_self
 from .prior import PriorDataLoader
 
 
+class _Deferred:
+    """Registry of device-side validity checks that a sampler could not finish without a host sync (e.g. the Cholesky
+    pivot flags of priors.fast_gp).  While `active`, samplers append a zero-argument callable instead of syncing; the
+    prefetching loader runs them when the batch is handed to the consumer — a full step later, when the flags have long
+    been copied to pinned host memory, so nothing stalls."""
+    active = False
+    pending = []
+
+    @classmethod
+    def collect(cls):
+        out, cls.pending = cls.pending, []
+        return out
+
+
+def prefetch_enabled(device_hint=None):
+    import os
+    return os.environ.get("PFN_B200_PREFETCH", "1") != "0" and torch.cuda.is_available()
+
+
+def _tensors_of(obj):
+    if torch.is_tensor(obj):
+        yield obj
+    elif isinstance(obj, (tuple, list)):
+        for o in obj:
+            yield from _tensors_of(o)
+
+
 def get_batch_to_dataloader(get_batch_method_):
     """Wrap a `get_batch(batch_size, seq_len, num_features, ...) -> (x, y, target_y)` function into a loader class
     that yields `num_steps` freshly sampled batches per epoch as `((x, y), target_y)` (reference :14-42)."""
@@ -36,8 +63,51 @@ def get_batch_to_dataloader(get_batch_method_):
         def __len__(self):
             return self.num_steps
 
+        def _produce(self):
+            return self.gbm(**self.get_batch_kwargs, fuse_x_y=self.fuse_x_y)
+
         def __iter__(self):
-            return iter(self.gbm(**self.get_batch_kwargs, fuse_x_y=self.fuse_x_y) for _ in range(self.num_steps))
+            """Yields `num_steps` fresh batches.  On CUDA the NEXT batch is sampled on a low-priority side stream while
+            the consumer works on the current one (sampling does not depend on the weights), and deferred sampler
+            checks are resolved at hand-off.  The reference builds every batch synchronously (priors/utils.py:36-37)."""
+            if not prefetch_enabled():
+                return iter(self._produce() for _ in range(self.num_steps))
+            return self._iter_prefetch()
+
+        def _iter_prefetch(self):
+            side = getattr(self, '_side_stream', None)
+            if side is None:
+                dev = self.get_batch_kwargs.get('device', None)
+                dev = torch.device(dev) if dev is not None and torch.device(dev).type == 'cuda' else torch.device('cuda', torch.cuda.current_device())
+                side = self._side_stream = torch.cuda.Stream(device=dev, priority=0)
+                self._side_device = dev
+
+            def launch():
+                prev = _Deferred.active
+                _Deferred.active = True
+                try:
+                    side.wait_stream(torch.cuda.current_stream(self._side_device))   # allocator reuse / ordering w.r.t. the consumer
+                    with torch.cuda.stream(side):
+                        batch = self._produce()
+                        ev = torch.cuda.Event()
+                        ev.record(side)
+                    checks = _Deferred.collect()
+                finally:
+                    _Deferred.active = prev
+                return batch, ev, checks
+
+            nxt = launch() if self.num_steps > 0 else None
+            for i in range(self.num_steps):
+                batch, ev, checks = nxt
+                nxt = launch() if i + 1 < self.num_steps else None
+                cur = torch.cuda.current_stream(self._side_device)
+                cur.wait_event(ev)
+                for t in _tensors_of(batch):
+                    if t.is_cuda:
+                        t.record_stream(cur)
+                for chk in checks:
+                    chk()
+                yield batch
 
     return DL
 

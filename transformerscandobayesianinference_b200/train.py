@@ -2,12 +2,18 @@
 
 Same signature, defaults, prints and return value `(total_loss, positional_losses, model_on_cpu)`.  Differences that
 do not change results: the model forward/backward and the criterion run on hand-written CUDA kernels; the mask is
-never built; per-step `.item()` syncs are replaced by on-device accumulation read once per epoch; under torchrun
-(WORLD_SIZE > 1) `batch_size` is the GLOBAL batch, sharded over ranks with one gradient all-reduce per optimizer
-step (parallel.py).
+never built; per-step `.item()` syncs are replaced by on-device accumulation read once per epoch; the prior loader
+samples the NEXT batch on a side stream while this step runs; under torchrun (WORLD_SIZE > 1) `batch_size` is the
+GLOBAL batch, sharded over ranks (each rank seeds its sampler differently) with one gradient all-reduce per
+optimizer step (parallel.py).
+
+`build_trainer(...)` returns the `Trainer` that `train()` drives; `bench.py` times exactly `Trainer.step`, i.e. the
+public path, not a re-implementation of it.
 """
+import inspect
 import time
 
+import numpy as np
 import torch
 from torch import nn
 
@@ -30,86 +36,140 @@ def _is_bar(criterion):
     return isinstance(criterion, BarDistribution) or "BarDistribution" in criterion.__class__.__name__
 
 
-def train(priordataloader_class, criterion, encoder_generator, emsize=200, nhid=200, nlayers=6, nhead=2, dropout=0.2,
-          epochs=10, steps_per_epoch=100, batch_size=200, bptt=10, lr=None, warmup_epochs=10, input_normalization=False,
-          y_encoder_generator=None, pos_encoder_generator=None, decoder=None, extra_prior_kwargs_dict={},
-          scheduler=get_cosine_schedule_with_warmup, load_weights_from_this_state_dict=None, validation_period=10,
-          single_eval_pos_gen=None, gpu_device='cuda:0', aggregate_k_gradients=1, verbose=True):
-    world = parallel.world_size()
-    if world > 1 and torch.cuda.is_available():
-        gpu_device = f'cuda:{torch.cuda.current_device()}'
-    device = gpu_device if torch.cuda.is_available() else 'cpu:0'
-    print(f'Using {device} device')
-    assert batch_size % world == 0, f'global batch {batch_size} must be divisible by the world size {world}'
-    local_batch = batch_size // world
-    dl = priordataloader_class(num_steps=steps_per_epoch, batch_size=local_batch, seq_len=bptt, **extra_prior_kwargs_dict)
+def _loader_accepts_device(priordataloader_class):
+    """True when the prior's `get_batch` takes a `device` keyword (all priors of this package do)."""
+    fn = getattr(priordataloader_class, 'get_batch_method', None)
+    if fn is None:
+        return False
+    try:
+        return 'device' in inspect.signature(fn).parameters
+    except (TypeError, ValueError):
+        return False
 
-    encoder = encoder_generator(dl.num_features + 1 if dl.fuse_x_y else dl.num_features, emsize)
-    n_out = dl.num_outputs
-    if isinstance(criterion, nn.GaussianNLLLoss):
-        n_out *= 2
-    elif _is_bar(criterion):
-        assert n_out == 1
-        n_out = criterion.num_bars
-    model = TransformerModel(encoder, n_out, emsize, nhead, nhid, nlayers, dropout,
-                             y_encoder=y_encoder_generator(1, emsize), input_normalization=input_normalization,
-                             pos_encoder=(pos_encoder_generator or positional_encodings.NoPositionalEncoding)(emsize, bptt * 2),
-                             decoder=decoder)
-    model.criterion = criterion
-    if load_weights_from_this_state_dict is not None:
-        model.load_state_dict(load_weights_from_this_state_dict)
-    model.to(device)
-    parallel.broadcast_parameters(model)
 
-    if lr is None:
-        lr = get_openai_lr(model)
-        print(f"Using OpenAI max lr of {lr}.")
-    on_cuda = torch.device(device).type == 'cuda'
-    optimizer = torch.optim.Adam(model.parameters(), lr=lr, **({'fused': True} if on_cuda else {}))
-    scheduler = scheduler(optimizer, warmup_epochs, epochs)
-    params = [p for p in model.parameters() if p.requires_grad]
+class Trainer:
+    """Everything `train()` builds (loader, model, criterion, optimizer, scheduler) plus the inner step
+    (reference train.py:58-110).  One instance per process / rank."""
 
-    def train_epoch():
+    def __init__(self, priordataloader_class, criterion, encoder_generator, emsize, nhid, nlayers, nhead, dropout,
+                 epochs, steps_per_epoch, batch_size, bptt, lr, warmup_epochs, input_normalization,
+                 y_encoder_generator, pos_encoder_generator, decoder, extra_prior_kwargs_dict, scheduler,
+                 load_weights_from_this_state_dict, single_eval_pos_gen, gpu_device, aggregate_k_gradients):
+        world = parallel.world_size()
+        if world > 1 and torch.cuda.is_available():
+            gpu_device = f'cuda:{torch.cuda.current_device()}'
+        device = gpu_device if torch.cuda.is_available() else 'cpu:0'
+        print(f'Using {device} device')
+        assert batch_size % world == 0, f'global batch {batch_size} must be divisible by the world size {world}'
+        self.world, self.rank = world, parallel.rank()
+        self.device = device
+        self.bptt = bptt
+        self.steps_per_epoch = steps_per_epoch
+        self.aggregate_k_gradients = aggregate_k_gradients
+        self.single_eval_pos_gen = single_eval_pos_gen
+        self.criterion = criterion
+        local_batch = batch_size // world
+        prior_kwargs = dict(extra_prior_kwargs_dict)
+        on_cuda = torch.device(device).type == 'cuda'
+        # the prior samples where the model lives (the reference priors default to `utils.default_device` = cuda:0, which
+        # is wrong for every rank but 0 and for gpu_device='cuda:1')
+        if on_cuda and 'device' not in prior_kwargs and _loader_accepts_device(priordataloader_class):
+            prior_kwargs['device'] = device
+        self.dl = priordataloader_class(num_steps=steps_per_epoch, batch_size=local_batch, seq_len=bptt, **prior_kwargs)
+        dl = self.dl
+
+        encoder = encoder_generator(dl.num_features + 1 if dl.fuse_x_y else dl.num_features, emsize)
+        n_out = dl.num_outputs
+        if isinstance(criterion, nn.GaussianNLLLoss):
+            n_out *= 2
+        elif _is_bar(criterion):
+            assert n_out == 1
+            n_out = criterion.num_bars
+        self.n_out = n_out
+        model = TransformerModel(encoder, n_out, emsize, nhead, nhid, nlayers, dropout,
+                                 y_encoder=y_encoder_generator(1, emsize), input_normalization=input_normalization,
+                                 pos_encoder=(pos_encoder_generator or positional_encodings.NoPositionalEncoding)(emsize, bptt * 2),
+                                 decoder=decoder)
+        model.criterion = criterion
+        if load_weights_from_this_state_dict is not None:
+            model.load_state_dict(load_weights_from_this_state_dict)
+        model.to(device)
+        parallel.broadcast_parameters(model)
+        self.model = model
+
+        if world > 1:
+            # Distinct prior draws per rank: every rank arrives here with the same torch / numpy generator state (same
+            # default seed or the same user seed), so shift each by the rank.  Python's `random` stays shared: it drives the
+            # single_eval_pos samplers, which must agree across ranks (and are broadcast per epoch anyway).
+            base = torch.initial_seed()
+            torch.manual_seed(base + self.rank)
+            np.random.seed((int(np.random.get_state()[1][0]) + self.rank) % (2 ** 32))
+
+        if lr is None:
+            lr = get_openai_lr(model)
+            print(f"Using OpenAI max lr of {lr}.")
+        self.optimizer = torch.optim.Adam(model.parameters(), lr=lr, **({'fused': True} if on_cuda else {}))
+        self.scheduler = scheduler(self.optimizer, warmup_epochs, epochs)
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        self._micro = 0
+
+    # ------------------------------------------------------------------------------------------------------------
+    def step(self, data, targets, single_eval_pos):
+        """One training step on one batch (reference train.py:64-97).  Returns (loss, losses) on the device; the
+        optimizer steps every `aggregate_k_gradients`-th call."""
+        device, criterion, model, n_out = self.device, self.criterion, self.model, self.n_out
+        data = tuple(e.to(device) for e in data) if isinstance(data, tuple) else data.to(device)
+        output = model(data, single_eval_pos=single_eval_pos)
+        self.forward_done_time = time.time()
+
+        if single_eval_pos is not None:
+            targets = targets[single_eval_pos:]
+        if isinstance(criterion, nn.GaussianNLLLoss):
+            assert output.shape[-1] == 2, \
+                'need to write a little bit of code to handle multiple regression targets at once'
+            mean_pred = output[..., 0]
+            var_pred = output[..., 1].abs()
+            losses = criterion(mean_pred.flatten(), targets.to(device).flatten(), var=var_pred.flatten())
+        elif isinstance(criterion, (nn.MSELoss, nn.BCEWithLogitsLoss)):
+            losses = criterion(output.flatten(), targets.to(device).flatten())
+        else:
+            losses = criterion(output.reshape(-1, n_out), targets.to(device).flatten())
+        losses = losses.view(*output.shape[0:2]).squeeze(-1)
+
+        loss = losses.mean()
+        loss.backward()
+        self._micro += 1
+        if self._micro % self.aggregate_k_gradients == 0:
+            parallel.allreduce_gradients(self.params)
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 1.)
+            self.optimizer.step()
+            self.optimizer.zero_grad()
+        return loss, losses
+
+    def draw_single_eval_positions(self, n):
+        """One single_eval_pos per global step, identical on every rank (reference train.py:69)."""
+        gen = self.single_eval_pos_gen
+        seps = [gen() if callable(gen) else gen for _ in range(n)]
+        return parallel.broadcast_object(seps)
+
+    def train_epoch(self):
+        model, dl, device, bptt = self.model, self.dl, self.device, self.bptt
         model.train()
         total_loss = torch.zeros((), device=device)
         pos_loss = torch.zeros(bptt, device=device)
         pos_count = torch.zeros(bptt, device=device)
         before_get_batch = time.time()
-        assert len(dl) % aggregate_k_gradients == 0, \
+        assert len(dl) % self.aggregate_k_gradients == 0, \
             'Please set the number of steps per epoch s.t. `aggregate_k_gradients` divides it.'
-        # one single_eval_pos per global step, identical on every rank (reference train.py:69)
-        seps = [single_eval_pos_gen() if callable(single_eval_pos_gen) else single_eval_pos_gen for _ in range(len(dl))]
-        seps = parallel.broadcast_object(seps)
+        seps = self.draw_single_eval_positions(len(dl))
         time_to_get_batch = forward_time = step_time = 0.
+        self._micro = 0
         for batch, (data, targets) in enumerate(dl):
             time_to_get_batch = time.time() - before_get_batch
             before_forward = time.time()
             single_eval_pos = seps[batch]
-            data = tuple(e.to(device) for e in data) if isinstance(data, tuple) else data.to(device)
-            output = model(data, single_eval_pos=single_eval_pos)
-            forward_time = time.time() - before_forward
-
-            if single_eval_pos is not None:
-                targets = targets[single_eval_pos:]
-            if isinstance(criterion, nn.GaussianNLLLoss):
-                assert output.shape[-1] == 2, \
-                    'need to write a little bit of code to handle multiple regression targets at once'
-                mean_pred = output[..., 0]
-                var_pred = output[..., 1].abs()
-                losses = criterion(mean_pred.flatten(), targets.to(device).flatten(), var=var_pred.flatten())
-            elif isinstance(criterion, (nn.MSELoss, nn.BCEWithLogitsLoss)):
-                losses = criterion(output.flatten(), targets.to(device).flatten())
-            else:
-                losses = criterion(output.reshape(-1, n_out), targets.to(device).flatten())
-            losses = losses.view(*output.shape[0:2]).squeeze(-1)
-
-            loss = losses.mean()
-            loss.backward()
-            if batch % aggregate_k_gradients == aggregate_k_gradients - 1:
-                parallel.allreduce_gradients(params)
-                torch.nn.utils.clip_grad_norm_(model.parameters(), 1.)
-                optimizer.step()
-                optimizer.zero_grad()
+            loss, losses = self.step(data, targets, single_eval_pos)
+            forward_time = self.forward_done_time - before_forward
             step_time = time.time() - before_forward
 
             ld = loss.detach()
@@ -122,12 +182,37 @@ def train(priordataloader_class, criterion, encoder_generator, emsize=200, nhid=
                 pos_count[single_eval_pos] += 1
             before_get_batch = time.time()
 
-        if _is_bar(criterion) and hasattr(criterion, 'check_support'):
-            criterion.check_support()
+        if _is_bar(self.criterion) and hasattr(self.criterion, 'check_support'):
+            self.criterion.check_support()
         total_loss = parallel.allreduce_mean_scalar(total_loss)
         pos_loss = parallel.allreduce_mean_scalar(pos_loss)
-        return (total_loss.item() / steps_per_epoch, (pos_loss / pos_count).tolist(), time_to_get_batch, forward_time,
-                step_time)
+        return (total_loss.item() / self.steps_per_epoch, (pos_loss / pos_count).tolist(), time_to_get_batch,
+                forward_time, step_time)
+
+
+def build_trainer(priordataloader_class, criterion, encoder_generator, emsize=200, nhid=200, nlayers=6, nhead=2,
+                  dropout=0.2, epochs=10, steps_per_epoch=100, batch_size=200, bptt=10, lr=None, warmup_epochs=10,
+                  input_normalization=False, y_encoder_generator=None, pos_encoder_generator=None, decoder=None,
+                  extra_prior_kwargs_dict={}, scheduler=get_cosine_schedule_with_warmup,
+                  load_weights_from_this_state_dict=None, validation_period=10, single_eval_pos_gen=None,
+                  gpu_device='cuda:0', aggregate_k_gradients=1, verbose=True):
+    """Same arguments as `train()`; returns the Trainer without running an epoch."""
+    return Trainer(priordataloader_class, criterion, encoder_generator, emsize, nhid, nlayers, nhead, dropout, epochs,
+                   steps_per_epoch, batch_size, bptt, lr, warmup_epochs, input_normalization, y_encoder_generator,
+                   pos_encoder_generator, decoder, extra_prior_kwargs_dict, scheduler,
+                   load_weights_from_this_state_dict, single_eval_pos_gen, gpu_device, aggregate_k_gradients)
+
+
+def train(priordataloader_class, criterion, encoder_generator, emsize=200, nhid=200, nlayers=6, nhead=2, dropout=0.2,
+          epochs=10, steps_per_epoch=100, batch_size=200, bptt=10, lr=None, warmup_epochs=10, input_normalization=False,
+          y_encoder_generator=None, pos_encoder_generator=None, decoder=None, extra_prior_kwargs_dict={},
+          scheduler=get_cosine_schedule_with_warmup, load_weights_from_this_state_dict=None, validation_period=10,
+          single_eval_pos_gen=None, gpu_device='cuda:0', aggregate_k_gradients=1, verbose=True):
+    tr = Trainer(priordataloader_class, criterion, encoder_generator, emsize, nhid, nlayers, nhead, dropout, epochs,
+                 steps_per_epoch, batch_size, bptt, lr, warmup_epochs, input_normalization, y_encoder_generator,
+                 pos_encoder_generator, decoder, extra_prior_kwargs_dict, scheduler, load_weights_from_this_state_dict,
+                 single_eval_pos_gen, gpu_device, aggregate_k_gradients)
+    model, dl, scheduler = tr.model, tr.dl, tr.scheduler
 
     total_loss = float('inf')
     total_positional_losses = float('inf')
@@ -136,7 +221,7 @@ def train(priordataloader_class, criterion, encoder_generator, emsize=200, nhid=
     try:
         for epoch in range(1, epochs + 1):
             epoch_start_time = time.time()
-            total_loss, total_positional_losses, time_to_get_batch, forward_time, step_time = train_epoch()
+            total_loss, total_positional_losses, time_to_get_batch, forward_time, step_time = tr.train_epoch()
             if hasattr(dl, 'validate') and epoch % validation_period == 0:
                 with torch.no_grad():
                     val_score = dl.validate(model)

@@ -111,7 +111,7 @@ class TransformerModel(nn.Module):
         params = []
         for layer in self.transformer_encoder.layers:
             params.extend(engine.layer_params(layer))
-        h = engine.EncoderStackFn.apply(h, T, B, sep, self.nhead, precision, *params)
+        h = engine.EncoderStackFn.apply(h, T, B, sep, self.nhead, precision, torch.is_grad_enabled(), *params)
 
         hq = h[sep * B:]
         if self._default_decoder():
