@@ -213,3 +213,28 @@ def gp_sample_ref(x, z, ls, os_, noise, kernel="rbf", jitter=0.0):
         K = K + jitter * torch.eye(K.shape[-1], dtype=K.dtype)
     L = torch.linalg.cholesky(K)
     return (L @ z.unsqueeze(-1)).squeeze(-1), L
+
+
+# --------------------------------------------------------------------------------------------------
+# exact-GP predictive baseline (reference priors/fast_gp.py:88-120): for every t, condition on rows < t and score row t
+# --------------------------------------------------------------------------------------------------
+def gp_exact_predictive_ref(x, y, lengthscale, outputscale, noise, use_mse=False):
+    """x [T,B,F], y [T,B] (float64 recommended) -> losses [T-1, B]: row k scores position t = k + 1 given rows < t, with
+    the Gaussian predictive of the noisy observation (`likelihood(model(x_t))`, constant zero mean, RBF kernel).
+    Straight per-t restatement (a fresh t x t solve for every t), sharing nothing with the one-factor device path."""
+    T, B, F = x.shape
+    xb, yb = x.transpose(0, 1), y.transpose(0, 1)
+    d2 = ((xb.unsqueeze(2) - xb.unsqueeze(1)) / lengthscale).pow(2).sum(-1)
+    K = outputscale * torch.exp(-0.5 * d2)
+    out = []
+    for t in range(1, T):
+        Ktt = K[:, :t, :t] + noise * torch.eye(t, dtype=K.dtype)
+        kst = K[:, :t, t]
+        sol = torch.linalg.solve(Ktt, torch.stack([yb[:, :t], kst], -1))      # [B,t,2]
+        mean = (kst * sol[..., 0]).sum(-1)
+        var = K[:, t, t] + noise - (kst * sol[..., 1]).sum(-1)
+        if use_mse:
+            out.append((mean - yb[:, t]) ** 2)
+        else:
+            out.append(0.5 * (math.log(2 * math.pi) + torch.log(var) + (yb[:, t] - mean) ** 2 / var))
+    return torch.stack(out)

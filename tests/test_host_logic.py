@@ -197,3 +197,24 @@ def test_wgrad_split_factors_fill_the_grid_once():
             assert 1 <= ks <= (n // 64) // 8
     finally:
         _lib.num_sms = saved
+
+
+def test_one_factor_exact_gp_predictive_identity():
+    """The identity priors.fast_gp.evaluate relies on: with L = chol(K + noise I) of the FULL matrix and alpha = L^-1 y,
+    the prefix-t Gaussian predictive NLL of row t is 1/2 log(2 pi) + log L_tt + alpha_t^2 / 2 (and the squared error of the
+    predictive mean is (L_tt alpha_t)^2) -- checked in fp64 against the per-t restatement of reference priors/fast_gp.py:95-116."""
+    import math
+    from oracle import pfn_oracle as O
+    torch.manual_seed(4)
+    T, B, F = 24, 3, 2
+    x, y = torch.rand(T, B, F, dtype=torch.float64), torch.randn(T, B, dtype=torch.float64)
+    ls, os_, noise = 0.4, 1.3, 0.05
+    K = O.gp_kernel_ref(x.transpose(0, 1), torch.full((B, F), ls, dtype=torch.float64), torch.full((B,), os_, dtype=torch.float64),
+                        torch.full((B,), noise, dtype=torch.float64))
+    Lf = torch.linalg.cholesky(K)
+    alpha = torch.linalg.solve_triangular(Lf, y.transpose(0, 1).unsqueeze(-1), upper=False).squeeze(-1)
+    d = torch.diagonal(Lf, dim1=1, dim2=2)
+    nll = (0.5 * math.log(2 * math.pi) + torch.log(d) + 0.5 * alpha ** 2)[:, 1:].transpose(0, 1)
+    mse = ((d * alpha) ** 2)[:, 1:].transpose(0, 1)
+    assert torch.allclose(nll, O.gp_exact_predictive_ref(x, y, ls, os_, noise), rtol=1e-9, atol=1e-9)
+    assert torch.allclose(mse, O.gp_exact_predictive_ref(x, y, ls, os_, noise, use_mse=True), rtol=1e-8, atol=1e-10)

@@ -25,6 +25,7 @@ SOURCES = [
     "attention_simt.cu",
     "attention_tc.cu",
     "attention_bwd_tc.cu",
+    "attention_bwd_dq.cu",
     "gp_sampler.cu",
 ]
 

@@ -80,6 +80,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Waiters that are NOT on the critical path (TMA producer waiting for a free ring stage, row warps waiting far ahead of the
+// tensor pipe) must not burn the issue slots of the scheduler they share with the MMA-issuing warp, nor hammer the
+// mbarrier unit: a spinning warp issues a probe + branch every few clocks.  `mbar_wait_suspend` uses the potentially
+// blocking mbarrier.try_wait (the hardware parks the warp; wake-up costs up to ~1000 clocks, measured), and
+// `mbar_wait_backoff` sleeps NS nanoseconds between probes after the first one failed.
+__device__ __forceinline__ void mbar_wait_suspend(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (++spins > PFN_MBAR_SPIN_LIMIT) { printf("pfn: mbarrier try_wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+  }
+}
+template <int NS>
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(NS);
+    if (++spins > PFN_MBAR_SPIN_LIMIT) { printf("pfn: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+  }
+}
+
 // Warp-granular variants: one lane polls / arrives on behalf of a CONVERGED warp.  Arrivals on one mbarrier serialise
 // (~5 clk each, measured), so 8 warp arrivals instead of 256 thread arrivals take ~1000 clocks off every hand-off.
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {

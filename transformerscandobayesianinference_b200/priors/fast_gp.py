@@ -129,36 +129,130 @@ DataLoader = get_batch_to_dataloader(get_batch)
 DataLoader.num_outputs = 1
 
 
+class _Predictive:
+    """The slice of gpytorch's MultivariateNormal the reference touches (priors/fast_gp.py:102-115): `.mean`,
+    `.covariance_matrix`, `.variance`, `.log_prob(y)` for batched predictions at ONE test point per dataset."""
+
+    def __init__(self, mean, var):
+        self.mean = mean                       # [B, 1]
+        self.variance = var                    # [B, 1]
+        self.covariance_matrix = var.unsqueeze(-1)   # [B, 1, 1]
+
+    def log_prob(self, value):
+        v = value.reshape(self.mean.shape).to(self.mean.dtype)
+        return (-0.5 * (math.log(2 * math.pi) + torch.log(self.variance) + (v - self.mean) ** 2 / self.variance)).sum(-1)
+
+
+class GaussianLikelihood:
+    """likelihood(f): adds the observation noise to the latent predictive (gpytorch GaussianLikelihood.__call__)."""
+
+    def __init__(self, noise):
+        self.noise = float(noise)
+
+    def eval(self):
+        return self
+
+    def __call__(self, f):
+        return _Predictive(f.mean, f.variance + self.noise)
+
+
+class ExactGPModel:
+    """Gpytorch-free stand-in for the reference's ExactGPModel (priors/fast_gp.py:13-32): constant zero mean,
+    outputscale * RBF(lengthscale) kernel, exact conditioning on (train_x [B,t,F], train_y [B,t]).  Calling the model on
+    test inputs [B,m,F] returns the latent predictive of each test point (batched closed form on the inputs' device)."""
+
+    def __init__(self, train_x, train_y, likelihood, lengthscale, outputscale):
+        self.train_x, self.train_y, self.likelihood = train_x, train_y, likelihood
+        self.lengthscale, self.outputscale = float(lengthscale), float(outputscale)
+
+    def eval(self):
+        return self
+
+    def to(self, device):
+        self.train_x, self.train_y = self.train_x.to(device), self.train_y.to(device)
+        return self
+
+    def _k(self, a, b):
+        d2 = ((a.unsqueeze(2) - b.unsqueeze(1)) / self.lengthscale).pow(2).sum(-1)
+        return self.outputscale * torch.exp(-0.5 * d2)
+
+    @torch.no_grad()
+    def __call__(self, x):
+        xt, yt = self.train_x.double(), self.train_y.double()
+        xs = x.to(xt.device).double()
+        t = xt.shape[1]
+        Ktt = self._k(xt, xt) + self.likelihood.noise * torch.eye(t, dtype=xt.dtype, device=xt.device)
+        Kst = self._k(xs, xt)                                   # [B,m,t]
+        chol = torch.linalg.cholesky(Ktt)
+        alpha = torch.cholesky_solve(yt.unsqueeze(-1), chol)    # [B,t,1]
+        v = torch.cholesky_solve(Kst.transpose(1, 2), chol)     # [B,t,m]
+        mean = (Kst @ alpha).squeeze(-1)
+        var = self.outputscale - (Kst * v.transpose(1, 2)).sum(-1)
+        return _Predictive(mean.float(), var.clamp_min(0).float())
+
+
+def get_model(x, y, hyperparameters):
+    """(model, likelihood) like the reference's `get_model` (priors/fast_gp.py:25-32), without gpytorch."""
+    hps = _hps_to_dict(hyperparameters)
+    likelihood = GaussianLikelihood(hps["noise"])
+    return ExactGPModel(x, y, likelihood, hps["lengthscale"], hps["outputscale"]), likelihood
+
+
+def get_model_on_device(x, y, hyperparameters, device):
+    model, likelihood = get_model(x, y, hyperparameters)
+    return model.to(device), likelihood
+
+
 @torch.no_grad()
 def evaluate(x, y, y_non_noisy, use_mse=False, hyperparameters={}, get_model_on_device=None, device=default_device,
              step_size=1, start_pos=0):
     """Exact-GP posterior baseline (reference :88-120): for each t, condition on rows < t and score row t with the
-    Gaussian predictive NLL (or MSE).  Restated with batched torch.linalg Cholesky solves on `device` — an
-    evaluation utility, not part of the training hot path.  Returns (all_losses [n_t, B], mean losses, seconds)."""
+    Gaussian predictive NLL (or MSE of the predictive mean).  Returns (all_losses [n_t, B], mean losses, seconds).
+
+    The reference builds and factors a fresh t x t model for EVERY t (T gpytorch models).  Here ONE Cholesky factor of the
+    full T x T kernel matrix per dataset answers all prefixes: the leading t x t block of L is the factor of the prefix
+    matrix, so with alpha = L^-1 y the prefix-t predictive of row t is
+        mean_t = y_t - L_tt alpha_t ,    var_t (incl. noise) = L_tt^2 ,    NLL_t = 1/2 log(2 pi) + log L_tt + alpha_t^2 / 2 .
+    The factor comes from the same fused sampler kernel that draws the prior (csrc/gp_sampler.cu).  A custom
+    `get_model_on_device` (e.g. a fitted model) falls back to the reference's per-t loop on top of that callable."""
     import time
     start = time.time()
     hps = _hps_to_dict(hyperparameters if hyperparameters else None)
-    dev = torch.device(device)
-    xb = x.to(dev, torch.float64).transpose(0, 1)            # [B,T,F]
-    yb = y.to(dev, torch.float64).transpose(0, 1)            # [B,T]
-    T = xb.shape[1]
-    d2 = ((xb.unsqueeze(2) - xb.unsqueeze(1)) / float(hps["lengthscale"])).pow(2).sum(-1)
-    K = float(hps["outputscale"]) * torch.exp(-0.5 * d2)
-    noise = float(hps["noise"])
+    if get_model_on_device is not None:
+        return _evaluate_per_t(x, y, use_mse, hps, get_model_on_device, device, step_size, start_pos, start)
+    dev = _compute_device(device)
+    xb = x.to(dev, torch.float32).transpose(0, 1).contiguous()            # [B,T,F]
+    yb = y.to(dev, torch.float32).transpose(0, 1).contiguous()            # [B,T]
+    Bn, T, F = xb.shape
+    ls = torch.full((Bn, F), float(hps["lengthscale"]), device=dev)
+    os_ = torch.full((Bn,), float(hps["outputscale"]), device=dev)
+    noise = torch.full((Bn,), float(hps["noise"]), device=dev)
+    _, Lf = sample_gp(xb, torch.zeros(Bn, T, device=dev), ls, os_, noise, L.KERNEL_RBF, return_factor=True)
+    alpha = torch.linalg.solve_triangular(Lf.double(), yb.double().unsqueeze(-1), upper=False).squeeze(-1)   # [B,T]
+    d = torch.diagonal(Lf, dim1=1, dim2=2).double()
+    if use_mse:
+        per_t = (d * alpha) ** 2
+    else:
+        per_t = 0.5 * math.log(2 * math.pi) + torch.log(d) + 0.5 * alpha ** 2
+    ts = list(range(max(start_pos, 1), T, step_size))
+    all_losses = per_t[:, ts].transpose(0, 1).float()                     # [n_t, B]
+    means_list = ([.0] if start_pos == 0 else []) + all_losses.mean(1).tolist()
+    return all_losses.to('cpu'), torch.tensor(means_list).to('cpu'), time.time() - start
+
+
+def _evaluate_per_t(x, y, use_mse, hps, get_model_on_device, device, step_size, start_pos, start):
+    import time
     means_list = [.0] if start_pos == 0 else []
     all_losses = []
-    for t in range(max(start_pos, 1), T, step_size):
-        Ktt = K[:, :t, :t] + noise * torch.eye(t, dtype=K.dtype, device=dev)
-        kst = K[:, :t, t]                                    # [B,t]
-        chol = torch.linalg.cholesky(Ktt)
-        alpha = torch.cholesky_solve(yb[:, :t].unsqueeze(-1), chol).squeeze(-1)
-        v = torch.cholesky_solve(kst.unsqueeze(-1), chol).squeeze(-1)
-        mean = (kst * alpha).sum(-1)
-        var = K[:, t, t] + noise - (kst * v).sum(-1)
+    for t in range(max(start_pos, 1), len(x), step_size):
+        model, likelihood = get_model_on_device(x[:t].transpose(0, 1), y[:t].transpose(0, 1), hps, device)
+        model.eval()
+        pred = likelihood(model(x[t].unsqueeze(1)))
+        means = pred.mean.squeeze()
         if use_mse:
-            ls = (mean - yb[:, t]) ** 2
+            ls = (means - y[t].to(means.device)) ** 2
         else:
-            ls = 0.5 * (math.log(2 * math.pi) + torch.log(var) + (yb[:, t] - mean) ** 2 / var)
+            ls = -pred.log_prob(y[t].to(means.device).unsqueeze(1))
         means_list.append(ls.mean().item())
-        all_losses.append(ls.float().flatten())
+        all_losses.append(ls.flatten().float())
     return torch.stack(all_losses).to('cpu'), torch.tensor(means_list).to('cpu'), time.time() - start

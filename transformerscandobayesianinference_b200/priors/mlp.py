@@ -80,6 +80,131 @@ def _order_groups_by_y(x, y):
     return xo, yo
 
 
+def _draw_model_specs(num_models, hyperparameters):
+    """Host-side scalar hyperparameters of every random MLP, drawn with the reference's samplers in the reference's
+    call order (priors/mlp.py:92-104: dropout_prob, noise_std, init_std, num_features_used, categorical spec, num_layers,
+    hidden_dim) for model 0, then model 1, ... (`models = [get_model() for _ in range(num_models)]`, :195)."""
+    (num_layers_sampler, hidden_dim_sampler, _act, init_std_sampler, noise_std_sampler, dropout_prob_sampler, _bin,
+     num_features_used_sampler, _causes, _is_causal, _psc, _psw, _yie, _oy, _nbuf, categorical_features_sampler_, _nan) = hyperparameters
+    specs = []
+    for _ in range(num_models):
+        sp = {"dropout_prob": float(dropout_prob_sampler()), "noise_std": float(noise_std_sampler()),
+              "init_std": float(init_std_sampler()), "num_features_used": int(num_features_used_sampler())}
+        sp["cat_features"], sp["cat_is_ordinal"] = categorical_features_sampler_(sp["num_features_used"])
+        sp["num_layers"] = int(num_layers_sampler())
+        sp["hidden_dim"] = int(hidden_dim_sampler())
+        assert sp["num_layers"] > 2
+        specs.append(sp)
+    return specs
+
+
+def _replay_hyperparameters(hyperparameters, specs):
+    """The same 17-tuple with the scalar samplers replaced by iterators over already-drawn `specs` (used when the
+    vectorised path bails out after the host draws were consumed, so that the per-model path sees the same models)."""
+    it = {k: iter([sp[k] for sp in specs]) for k in ("dropout_prob", "noise_std", "init_std", "num_features_used", "num_layers", "hidden_dim")}
+    cats = iter([(sp["cat_features"], sp["cat_is_ordinal"]) for sp in specs])
+    hp = list(hyperparameters)
+    hp[0] = lambda: next(it["num_layers"])
+    hp[1] = lambda: next(it["hidden_dim"])
+    hp[3] = lambda: next(it["init_std"])
+    hp[4] = lambda: next(it["noise_std"])
+    hp[5] = lambda: next(it["dropout_prob"])
+    hp[7] = lambda: next(it["num_features_used"])
+    hp[15] = lambda n: next(cats)
+    return tuple(hp)
+
+
+def _get_batch_vectorized(specs, g, seq_len, num_features, device, hyperparameters, sampling, num_outputs):
+    """All `len(specs)` random MLPs x `g` datasets each as one chain of batched device ops (non-causal prior without
+    categorical features, reference priors/mlp.py:113-189 per dataset).  Models differ in input width, hidden width,
+    init / noise scale and sparsity: tensors are padded to the batch maxima and masked, models with different depth form
+    separate groups.  Distribution per dataset is the reference's: weights and biases ~ N(0, (init_std/(1-p))^2) *
+    Bernoulli(1-p) (p = 0 for the first weight matrix, :126-130), causes ~ N(0,1) / U(0,1) (:133-141), Gaussian noise of
+    std noise_std after every layer but the first (:113-121), x = causes, y = last output (:157-158), normalisation over the
+    sequence (:177), median binarisation per dataset (:180), optional /(used/num_features) (:182-183), optional order_by_y
+    with one `random.randint` sign per dataset (:185-186), zero padding to num_features (:189)."""
+    activation_module, is_binary_classification, order_y = hyperparameters[2], hyperparameters[6], hyperparameters[13]
+    normalize_by_used = hyperparameters[14]
+    dev = torch.device(device)
+    M, T = len(specs), seq_len
+    out_x = torch.zeros(T, M * g, num_features, device=dev)
+    out_y = torch.empty(T, M * g, device=dev)
+    act = activation_module()
+    signs = None
+    if is_binary_classification and order_y:     # one host draw per dataset, dataset-major like the reference's sample loop
+        signs = torch.tensor([1.0 if random.randint(0, 1) else -1.0 for _ in range(M * g)], dtype=torch.float32)
+        signs = (signs.pin_memory() if dev.type == 'cuda' else signs).to(dev, non_blocking=True)
+    by_depth = {}
+    for mi, sp in enumerate(specs):
+        by_depth.setdefault(sp["num_layers"], []).append(mi)
+    for depth, idxs in by_depth.items():
+        m = len(idxs)
+        used = torch.tensor([specs[i]["num_features_used"] for i in idxs])
+        hid = torch.tensor([specs[i]["hidden_dim"] for i in idxs])
+        C, Hd = int(used.max()), int(hid.max())
+        host = torch.stack([used.float(), hid.float(),
+                            torch.tensor([specs[i]["init_std"] for i in idxs]),
+                            torch.tensor([specs[i]["noise_std"] for i in idxs]),
+                            torch.tensor([specs[i]["dropout_prob"] for i in idxs])])
+        host = (host.pin_memory() if dev.type == 'cuda' else host).to(dev, non_blocking=True)
+        used_d, hid_d, init_std, noise_std, p_drop = host[0], host[1], host[2], host[3], host[4]
+        cmask = (torch.arange(C, device=dev).view(1, C) < used_d.view(m, 1)).float()        # [m, C]
+        hmask = (torch.arange(Hd, device=dev).view(1, Hd) < hid_d.view(m, 1)).float()       # [m, Hd]
+        scale = (init_std / (1. - p_drop)).view(m, 1, 1)
+        keep = (1. - p_drop).view(m, 1, 1)
+
+        def param(shape_tail, first, mask):
+            w = torch.randn((m,) + shape_tail, device=dev)
+            if first:
+                w = w * init_std.view(m, 1, 1)                                                # p = 0 for the first tensor (:127)
+            else:
+                w = w * scale * torch.bernoulli(keep.expand((m,) + shape_tail))
+            return w * mask
+        # layer 0: Linear(c -> h); layers 1 .. depth-2: Linear(h -> h); last: Linear(h -> num_outputs)
+        W = [param((Hd, C), True, hmask.view(m, Hd, 1) * cmask.view(m, 1, C))]
+        b = [param((1, Hd), False, hmask.view(m, 1, Hd))]
+        for li in range(1, depth):
+            last = li == depth - 1
+            od = num_outputs if last else Hd
+            omask = torch.ones(m, od, device=dev) if last else hmask
+            W.append(param((od, Hd), False, omask.view(m, od, 1) * hmask.view(m, 1, Hd)))
+            b.append(param((1, od), False, omask.view(m, 1, od)))
+        if sampling == 'normal':
+            c = torch.randn(m, T * g, C, device=dev)
+        elif sampling == 'uniform':
+            c = torch.rand(m, T * g, C, device=dev)
+        else:
+            raise ValueError(f'Sampling is set to invalid setting: {sampling}.')
+        c = c * cmask.view(m, 1, C)
+        h = torch.baddbmm(b[0], c, W[0].transpose(1, 2))                                      # [m, T*g, Hd]
+        for li in range(1, depth):
+            h = torch.baddbmm(b[li], act(h), W[li].transpose(1, 2))
+            h = h + torch.randn_like(h) * noise_std.view(m, 1, 1)
+            if li < depth - 1:
+                h = h * hmask.view(m, 1, Hd)
+        # rows of the (T*g) axis are (t, dataset-in-group) pairs: -> [T, m, g, .]
+        y = h.view(m, T, g, num_outputs)[..., 0].permute(1, 0, 2)                             # [T, m, g]
+        x = c.view(m, T, g, C).permute(1, 0, 2, 3)                                            # [T, m, g, C]
+        x = (x - x.mean(0)) / (x.std(0) + .000001)                                            # padded columns stay 0
+        y = (y - y.mean(0)) / (y.std(0) + .000001)
+        if is_binary_classification:
+            med = torch.median(y, dim=0, keepdim=True)[0]                                     # lower median per dataset (Binarize)
+            y = (y > med).float()
+        if normalize_by_used:
+            x = x / (used_d / num_features).view(1, m, 1, 1)
+        cols = torch.tensor([i * g + k for i in idxs for k in range(g)], device=dev)
+        x = x.reshape(T, m * g, C)
+        y = y.reshape(T, m * g)
+        if signs is not None:
+            order = torch.argsort(y * signs[cols].view(1, -1), dim=0)                         # [T, m*g]
+            order = order.reshape(2, -1, m * g).transpose(0, 1).reshape(T, m * g)             # interleave the two halves
+            x = torch.gather(x, 0, order.unsqueeze(-1).expand(-1, -1, C))
+            y = torch.gather(y, 0, order)
+        out_x[:, cols, :C] = x
+        out_y[:, cols] = y
+    return out_x, out_y, out_y
+
+
 def get_batch(batch_size, seq_len, num_features, device=default_device,
               hyperparameters=(DEFAULT_NUM_LAYERS, DEFAULT_HIDDEN_DIM, DEFAULT_ACTIVATION_MODULE, DEFAULT_INIT_STD,
                                DEFAULT_HIDDEN_NOISE_STD, DEFAULT_FIXED_DROPOUT, DEFAULT_IS_BINARY_CLASSIFICATION),
@@ -99,6 +224,17 @@ def get_batch(batch_size, seq_len, num_features, device=default_device,
         'Please choose a batch_size divisible by batch_size_per_gp_sample.'
     num_models = sample_batch_size // batch_size_per_gp_sample
     g = batch_size_per_gp_sample
+
+    if not is_causal and torch.device(device).type == 'cuda':
+        # every model of the batch in ONE chain of batched device ops (the shipped BNN-prior configuration)
+        spec = _draw_model_specs(num_models, hyperparameters)
+        if not any(len(sp["cat_features"]) for sp in spec):
+            return _get_batch_vectorized(spec, g, seq_len, num_features, device, hyperparameters, sampling, num_outputs)
+        hyperparameters = _replay_hyperparameters(hyperparameters, spec)   # the host draws were consumed: replay them
+        (num_layers_sampler, hidden_dim_sampler, activation_module, init_std_sampler, noise_std_sampler,
+         dropout_prob_sampler, is_binary_classification, num_features_used_sampler, causes_sampler, is_causal,
+         pre_sample_causes, pre_sample_weights, y_is_effect, order_y, normalize_by_used_features,
+         categorical_features_sampler_, nan_prob) = hyperparameters
 
     def sample_model():
         dropout_prob = dropout_prob_sampler()
