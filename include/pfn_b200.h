@@ -81,6 +81,11 @@ typedef struct pfn_attn_desc {
   void* dqkv; int ld_dqkv;
   float* delta;            /* [B*H, T] fp32 scratch for backward: rowsum(dO * O) */
   int batch_major;         /* 0: token row = t*B + b (reference layout); 1: token row = b*T + t (tcgen05 kernels only) */
+  /* dropout on the attention probabilities (torch:nn/functional.py multi_head_attention_forward `dropout_p`; reference
+   * train.py:22 default 0.2): drop_thr = round(256 p) in [0,255], 0 = off; the keep bit of (row i, key j) of head (b,h) is
+   * pfn_dropout_keep_mask's bit for (row = (b*H + h)*T + i, col = j) under drop_seed.  fp32-FMA kernels only. */
+  uint32_t drop_seed;
+  int drop_thr;
 } pfn_attn_desc;
 
 int pfn_attention_fwd_simt(const pfn_attn_desc* d, void* stream);
@@ -113,6 +118,18 @@ int pfn_layernorm_fwd(const void* z, int ldz, const float* gamma, const float* b
 int pfn_layernorm_bwd(const void* dh, int lddh, const void* z, int ldz, const float* mean, const float* rstd,
                       const float* gamma, void* dz, int lddz, float* dgamma, float* dbeta, float* colsum_out, int rows,
                       int E, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Elementwise dropout (+ residual) with a regenerated counter-based mask (csrc/dropout.cuh):
+ *   out[r,c] = (keep(seed,r,c) ? x[r,c] * 256/(256-thr) : 0) + (residual ? residual[r,c] : 0)
+ * in place when out == x.  Replaces torch:nn/modules/transformer.py:961-982 dropout1 / dropout / dropout2 of the encoder
+ * layer in forward, and is applied to the incoming gradient with the same (seed, thr) in backward.  cols % 8 == 0.
+ * pfn_dropout_keep_mask writes the keep bits (1/0) of a rows x cols site as bytes: the hook that lets a test's oracle
+ * consume exactly the mask the kernels use (attention site: row = (b*H + h)*T + i, col = key j).
+ * ---------------------------------------------------------------------------------------------- */
+int pfn_dropout(const void* x, int ldx, const void* residual, int ldr, void* out, int ldo, int rows, int cols, int dtype,
+                uint32_t seed, int thr, void* stream);
+int pfn_dropout_keep_mask(uint8_t* out, int rows, int cols, uint32_t seed, int thr, void* stream);
 
 /* column sums: out[n] += sum_m X[m,n]   (bias gradients; torch autograd of addmm bias) */
 int pfn_colsum(const void* X, int ld, int dtype, float* out, int rows, int N, void* stream);

@@ -238,3 +238,26 @@ def gp_exact_predictive_ref(x, y, lengthscale, outputscale, noise, use_mse=False
         else:
             out.append(0.5 * (math.log(2 * math.pi) + torch.log(var) + (yb[:, t] - mean) ** 2 / var))
     return torch.stack(out)
+
+
+# --------------------------------------------------------------------------------------------------
+# encoder layer with dropout at the reference's four sites (torch nn/modules/transformer.py:961-982;
+# torch nn/functional.py multi_head_attention_forward `dropout_p`), the masks being GIVEN
+# --------------------------------------------------------------------------------------------------
+def encoder_layer_dropout_ref(h, lp, T, B, nhead, sep, keep, scale):
+    """Post-norm layer in training mode.  keep: dict of 0/1 tensors -- "attn" [B*H, T, T] (on the softmax probabilities),
+    "out" [T*B, E] (dropout1), "gelu" [T*B, nhid] (after the activation), "mlp" [T*B, E] (dropout2); kept entries are
+    multiplied by `scale` = 1 / (1 - p)."""
+    E = h.shape[1]
+    dh = E // nhead
+    qkv = h @ lp["in_w"].T + lp["in_b"]
+    q, k, v = qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:]
+    heads = lambda t: t.reshape(T, B, nhead, dh).permute(1, 2, 0, 3)            # [B,H,T,dh]
+    scores = heads(q) @ heads(k).transpose(-1, -2) / math.sqrt(dh) + d_q_mask(T, T - sep, dtype=h.dtype)
+    probs = torch.softmax(scores, -1) * keep["attn"].reshape(B, nhead, T, T).to(h.dtype) * scale
+    a = (probs @ heads(v)).permute(2, 0, 1, 3).reshape(T * B, E)
+    a = a @ lp["out_w"].T + lp["out_b"]
+    h1 = layernorm_ref(h + a * keep["out"].to(h.dtype) * scale, lp["g1"], lp["be1"])
+    g = gelu_erf(h1 @ lp["w1"].T + lp["b1"]) * keep["gelu"].to(h.dtype) * scale
+    m = g @ lp["w2"].T + lp["b2"]
+    return layernorm_ref(h1 + m * keep["mlp"].to(h.dtype) * scale, lp["g2"], lp["be2"])

@@ -42,6 +42,7 @@ class AttnDesc(ctypes.Structure):
         ("dout", c_void_p), ("ld_dout", c_int),
         ("dqkv", c_void_p), ("ld_dqkv", c_int),
         ("delta", c_void_p), ("batch_major", c_int),
+        ("drop_seed", ctypes.c_uint32), ("drop_thr", c_int),
     ]
 
 
@@ -54,6 +55,7 @@ EXPORTED_SYMBOLS = [
     "pfn_layernorm_fwd", "pfn_layernorm_bwd", "pfn_colsum",
     "pfn_bar_nll_fwd", "pfn_bar_nll_bwd", "pfn_bar_bucket_idx",
     "pfn_gp_sample",
+    "pfn_dropout", "pfn_dropout_keep_mask",
 ]
 
 _lib = None
@@ -122,6 +124,9 @@ def load():
     lib.pfn_bar_bucket_idx.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]
     lib.pfn_gp_sample.argtypes = [c_void_p] * 5 + [c_float, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                   c_void_p]
+    lib.pfn_dropout.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, ctypes.c_uint32, c_int,
+                                c_void_p]
+    lib.pfn_dropout_keep_mask.argtypes = [c_void_p, c_int, c_int, ctypes.c_uint32, c_int, c_void_p]
     _lib = lib
     return lib
 
@@ -260,8 +265,15 @@ def tc_gemm_ok(A, B, C, aux=None, C2=None):
     return C.stride(0) % cmul == 0 and C.data_ptr() % 16 == 0
 
 
-def attention_desc(qkv, out, lse, T, B, H, dh, sep, dout=None, dqkv=None, delta=None, batch_major=False):
+def drop_threshold(p):
+    """round(256 p) clipped to [0, 255]: the byte threshold of the counter-based dropout masks (csrc/dropout.cuh)."""
+    return max(0, min(255, int(round(256.0 * float(p)))))
+
+
+def attention_desc(qkv, out, lse, T, B, H, dh, sep, dout=None, dqkv=None, delta=None, batch_major=False, drop=None):
     d = AttnDesc()
+    if drop is not None:
+        d.drop_seed, d.drop_thr = int(drop[0]) & 0xFFFFFFFF, int(drop[1])
     d.batch_major = int(batch_major)
     d.T, d.B, d.H, d.dh, d.sep = T, B, H, dh, sep
     d.dtype = dtype_code(qkv)
@@ -281,25 +293,26 @@ def tc_attention_ok(qkv, dh, T=None):
 
 
 @_guarded
-def attention_fwd(qkv, out, lse, T, B, H, dh, sep, use_tc=None, batch_major=False):
+def attention_fwd(qkv, out, lse, T, B, H, dh, sep, use_tc=None, batch_major=False, drop=None):
+    """drop = (seed, thr): dropout on the attention probabilities (fp32-FMA kernels only; thr 0 / None = off)."""
     _count(1)
     lib = load()
     require_cuda(qkv, out, lse)
-    d = attention_desc(qkv, out, lse, T, B, H, dh, sep, batch_major=batch_major)
+    d = attention_desc(qkv, out, lse, T, B, H, dh, sep, batch_major=batch_major, drop=drop)
     if use_tc is None:
-        use_tc = tc_attention_ok(qkv, dh)
+        use_tc = tc_attention_ok(qkv, dh) and not (drop and drop[1] > 0)
     fn = lib.pfn_attention_fwd_tc if use_tc else lib.pfn_attention_fwd_simt
     check(fn(ctypes.byref(d), stream_ptr()), "pfn_attention_fwd")
 
 
 @_guarded
-def attention_bwd(qkv, out, lse, dout, dqkv, delta, T, B, H, dh, sep, use_tc=None, batch_major=False):
+def attention_bwd(qkv, out, lse, dout, dqkv, delta, T, B, H, dh, sep, use_tc=None, batch_major=False, drop=None):
     _count(2)
     lib = load()
     require_cuda(qkv, out, lse, dout, dqkv, delta)
-    d = attention_desc(qkv, out, lse, T, B, H, dh, sep, dout, dqkv, delta, batch_major=batch_major)
+    d = attention_desc(qkv, out, lse, T, B, H, dh, sep, dout, dqkv, delta, batch_major=batch_major, drop=drop)
     if use_tc is None:
-        use_tc = tc_attention_ok(qkv, dh)
+        use_tc = tc_attention_ok(qkv, dh) and not (drop and drop[1] > 0)
     fn = lib.pfn_attention_bwd_tc if use_tc else lib.pfn_attention_bwd_simt
     check(fn(ctypes.byref(d), stream_ptr()), "pfn_attention_bwd")
 
@@ -375,6 +388,26 @@ def bar_bucket_idx(y, borders, n_bars, idx):
     require_cuda(y, borders, idx)
     check(load().pfn_bar_bucket_idx(ptr(y), ptr(borders), n_bars, ptr(idx), y.numel(), stream_ptr()),
           "pfn_bar_bucket_idx")
+
+
+@_guarded
+def dropout(x, out, seed, thr, residual=None):
+    """out = dropout(x) (+ residual), mask regenerated from (seed, thr); in place when out is x."""
+    _count(1)
+    require_cuda(x, out, residual)
+    rows, cols = x.shape
+    assert out.shape == x.shape and out.dtype == x.dtype and (residual is None or residual.dtype == x.dtype)
+    check(load().pfn_dropout(ptr(x), x.stride(0), ptr(residual), residual.stride(0) if residual is not None else 0, ptr(out),
+                             out.stride(0), rows, cols, dtype_code(x), int(seed) & 0xFFFFFFFF, int(thr), stream_ptr()), "pfn_dropout")
+
+
+@_guarded
+def dropout_keep_mask(out, seed, thr):
+    """out [rows, cols] uint8 <- keep bits of the site (tests: lets the oracle consume the kernels' mask)."""
+    _count(1)
+    require_cuda(out)
+    rows, cols = out.shape
+    check(load().pfn_dropout_keep_mask(ptr(out), rows, cols, int(seed) & 0xFFFFFFFF, int(thr), stream_ptr()), "pfn_dropout_keep_mask")
 
 
 @_guarded

@@ -623,6 +623,7 @@ using namespace pfn;
 extern "C" int pfn_attention_bwd_tc(const pfn_attn_desc* d, void* stream) {
   if (int rc = check_attn_desc_public(d, true, "attention_bwd_tc")) return rc;
   PFN_CHECK_ARG(d->dtype == PFN_BF16, "attention_bwd_tc: bf16 only");
+  PFN_CHECK_ARG(d->drop_thr == 0, "attention_bwd_tc: attention-probability dropout is implemented by the fp32-FMA kernels only");
   PFN_CHECK_ARG(d->dh == AB_DH, "attention_bwd_tc: head dim %d unsupported (built for 128)", d->dh);
   PFN_CHECK_ARG(d->ld_qkv % 8 == 0 && d->ld_out % 8 == 0 && d->ld_dout % 8 == 0 && d->ld_dqkv % 8 == 0,
                 "attention_bwd_tc: leading dims must be multiples of 8");

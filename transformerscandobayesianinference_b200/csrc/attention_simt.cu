@@ -3,6 +3,7 @@
 // lanes, scores are reduced with warp shuffles, softmax is computed online.  The single_eval_pos mask of
 // reference transformer.py:35-41 is implicit:  keys(i) = [0, sep)  U  {i if i >= sep}.
 #include "common.cuh"
+#include "dropout.cuh"
 #include "../../include/pfn_b200.h"
 
 namespace pfn {
@@ -57,12 +58,13 @@ attn_fwd_simt_kernel(const pfn_attn_desc d) {
       const float m_new = fmaxf(m, s);
       const float corr = expf(m - m_new);
       const float p = expf(s - m_new);
-      l = l * corr + p;
+      l = l * corr + p;                 // the softmax normaliser is over ALL visible keys; dropout acts on the probabilities
+      const float pd = (d.drop_thr > 0 && !drop_keep(d.drop_seed, static_cast<uint32_t>(bh) * d.T + i, j, d.drop_thr)) ? 0.f : p;
 #pragma unroll
-      for (int c = 0; c < DPL; ++c) o[c] = fmaf(p, v[c], o[c] * corr);
+      for (int c = 0; c < DPL; ++c) o[c] = fmaf(pd, v[c], o[c] * corr);
       m = m_new;
     }
-    const float inv_l = 1.0f / l;
+    const float inv_l = (d.drop_thr > 0 ? drop_scale(d.drop_thr) : 1.0f) / l;
 #pragma unroll
     for (int c = 0; c < DPL; ++c) o[c] *= inv_l;
     store_head<T, DPL>(out + (static_cast<size_t>(i) * d.B + b) * d.ld_out + h * d.dh, d.dh, lane, o);
@@ -110,13 +112,15 @@ attn_bwd_dq_simt_kernel(const pfn_attn_desc d, float* __restrict__ delta) {
       s = warp_sum(s) * d.scale;
       dp = warp_sum(dp);
       const float p = expf(s - lse);
-      const float ds = p * (dp - dl) * d.scale;
+      // dropout on the probabilities: Pd = P m / (1 - p_drop);  dP = m dPd / (1 - p_drop);  dS = P (dP - delta)
+      const float mk = d.drop_thr > 0 ? (drop_keep(d.drop_seed, static_cast<uint32_t>(bh) * d.T + i, j, d.drop_thr) ? drop_scale(d.drop_thr) : 0.f) : 1.f;
+      const float ds = p * (mk * dp - dl) * d.scale;
 #pragma unroll
       for (int c = 0; c < DPL; ++c) dq[c] = fmaf(ds, k[c], dq[c]);
       if (jj >= d.sep) {
         float dk[DPL], dv[DPL];
 #pragma unroll
-        for (int c = 0; c < DPL; ++c) { dk[c] = ds * q[c]; dv[c] = p * dO[c]; }
+        for (int c = 0; c < DPL; ++c) { dk[c] = ds * q[c]; dv[c] = p * mk * dO[c]; }
         store_head<T, DPL>(dqkv + tok * d.ld_dqkv + E + h * d.dh, d.dh, lane, dk);
         store_head<T, DPL>(dqkv + tok * d.ld_dqkv + 2 * E + h * d.dh, d.dh, lane, dv);
       }
@@ -157,9 +161,10 @@ attn_bwd_dkv_simt_kernel(const pfn_attn_desc d, const float* __restrict__ delta)
       s = warp_sum(s) * d.scale;
       dp = warp_sum(dp);
       const float p = expf(s - d.lse[static_cast<size_t>(bh) * d.T + i]);
-      const float ds = p * (dp - delta[static_cast<size_t>(bh) * d.T + i]) * d.scale;
+      const float mk = d.drop_thr > 0 ? (drop_keep(d.drop_seed, static_cast<uint32_t>(bh) * d.T + i, j, d.drop_thr) ? drop_scale(d.drop_thr) : 0.f) : 1.f;
+      const float ds = p * (mk * dp - delta[static_cast<size_t>(bh) * d.T + i]) * d.scale;
 #pragma unroll
-      for (int c = 0; c < DPL; ++c) { dv[c] = fmaf(p, dO[c], dv[c]); dk[c] = fmaf(ds, q[c], dk[c]); }
+      for (int c = 0; c < DPL; ++c) { dv[c] = fmaf(p * mk, dO[c], dv[c]); dk[c] = fmaf(ds, q[c], dk[c]); }
     }
     store_head<T, DPL>(dqkv + tokj * d.ld_dqkv + E + h * d.dh, d.dh, lane, dk);
     store_head<T, DPL>(dqkv + tokj * d.ld_dqkv + 2 * E + h * d.dh, d.dh, lane, dv);
@@ -174,6 +179,7 @@ static int check_attn_desc(const pfn_attn_desc* d, bool bwd, const char* who) {
   PFN_CHECK_ARG(d->dtype == PFN_F32 || d->dtype == PFN_BF16, "%s: bad dtype %d", who, d->dtype);
   PFN_CHECK_ARG(d->qkv && d->out && d->lse, "%s: null qkv/out/lse", who);
   PFN_CHECK_ARG(d->batch_major == 0 || d->batch_major == 1, "%s: bad batch_major %d", who, d->batch_major);
+  PFN_CHECK_ARG(d->drop_thr >= 0 && d->drop_thr <= 255, "%s: dropout threshold %d outside [0,255]", who, d->drop_thr);
   PFN_CHECK_ARG(d->ld_qkv >= 3 * d->H * d->dh && d->ld_out >= d->H * d->dh, "%s: leading dims too small", who);
   if (bwd) {
     PFN_CHECK_ARG(d->dout && d->dqkv && d->delta, "%s: null dout/dqkv/delta", who);

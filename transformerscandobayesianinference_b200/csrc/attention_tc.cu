@@ -441,6 +441,7 @@ using namespace pfn;
 extern "C" int pfn_attention_fwd_tc(const pfn_attn_desc* d, void* stream) {
   if (int rc = check_attn_desc_public(d, false, "attention_fwd_tc")) return rc;
   if (int rc = check_tc_attn(d, "attention_fwd_tc")) return rc;
+  PFN_CHECK_ARG(d->drop_thr == 0, "attention_fwd_tc: attention-probability dropout is implemented by the fp32-FMA kernels only");
   CUtensorMap tmQ, tmKV;
   const int E = d->H * d->dh;
   if (int rc = make_qkv_map(&tmQ, d->qkv, d->ld_qkv, 3 * E, d->B, d->T, ATT_BM, d->batch_major)) return rc;

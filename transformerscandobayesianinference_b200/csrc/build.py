@@ -27,6 +27,7 @@ SOURCES = [
     "attention_bwd_tc.cu",
     "attention_bwd_dq.cu",
     "gp_sampler.cu",
+    "dropout.cu",
 ]
 
 NVCC_FLAGS = [

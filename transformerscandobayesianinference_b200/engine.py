@@ -49,6 +49,12 @@ def _wgrad_splits(n_tokens, out_rows, out_cols):
     return max(1, min(want, num_kb // 8 if num_kb >= 16 else 1))
 
 
+def site_seed(seed, layer, site):
+    """Seed of one dropout site (0 attention probabilities, 1 attention block output, 2 after GELU, 3 MLP block output)
+    of one layer, derived from the step's seed."""
+    return (int(seed) + 0x9E3779B9 * (4 * layer + site + 1)) & 0xFFFFFFFF
+
+
 def _cast(w, dtype):
     w = w.detach()
     return w.contiguous() if w.dtype == dtype else w.to(dtype).contiguous()
@@ -84,9 +90,13 @@ class EncoderStackFn(torch.autograd.Function):
     """src [T*B, E] (activation dtype) -> output of `nlayers` post-norm encoder layers under the sep mask."""
 
     @staticmethod
-    def forward(ctx, src, T, B, sep, nhead, precision, keep, *params):
+    def forward(ctx, src, T, B, sep, nhead, precision, keep, drop, *params):
         """`keep`: the CALLER's grad mode (torch.is_grad_enabled() outside this Function — inside it is always off, and
-        ctx.needs_input_grad does not reflect no_grad); when False no activation is retained (inference memory)."""
+        ctx.needs_input_grad does not reflect no_grad); when False no activation is retained (inference memory).
+        `drop`: None or (seed, thr) — training-mode dropout with probability thr/256 at the reference layer's four sites
+        (attention probabilities, attention block output, after the GELU, MLP block output; torch
+        nn/modules/transformer.py:961-982).  Masks are counter-based and regenerated in backward (csrc/dropout.cuh); the
+        attention-probability site runs on the fp32-FMA attention kernels."""
         L.require_cuda(src, *params)
         dt = act_dtype(precision)
         assert src.dtype == dt and src.dim() == 2
@@ -96,20 +106,30 @@ class EncoderStackFn(torch.autograd.Function):
         keep = bool(keep) and any(ctx.needs_input_grad)
         saved = []
         h = src.contiguous()
+        thr = drop[1] if drop else 0
         for li in range(n_layers):
             P = dict(zip(LAYER_PARAM_NAMES, params[li * N_LAYER_PARAMS:(li + 1) * N_LAYER_PARAMS]))
             in_w, out_w, w1, w2 = (_cast(P[k], dt) for k in ("in_w", "out_w", "w1", "w2"))
             qkv = _linear_fwd(h, in_w, P["in_b"])
             attn = torch.empty(N, E, device=h.device, dtype=dt)
             lse = torch.empty(B * nhead, T, device=h.device, dtype=torch.float32)
-            L.attention_fwd(qkv, attn, lse, T, B, nhead, dh, sep)
-            z1 = _linear_fwd(attn, out_w, P["out_b"], aux=h)
+            L.attention_fwd(qkv, attn, lse, T, B, nhead, dh, sep, drop=(site_seed(drop[0], li, 0), thr) if thr else None)
+            if thr:
+                z1 = _linear_fwd(attn, out_w, P["out_b"])
+                L.dropout(z1, z1, site_seed(drop[0], li, 1), thr, residual=h)           # h + dropout1(attn block)
+            else:
+                z1 = _linear_fwd(attn, out_w, P["out_b"], aux=h)
             h1 = torch.empty_like(z1)
             mean1 = torch.empty(N, device=h.device, dtype=torch.float32)
             rstd1 = torch.empty_like(mean1)
             L.layernorm_fwd(z1, P["g1"], P["be1"], h1, mean1, rstd1, LN_EPS)
             g, u = _linear_fwd(h1, w1, P["b1"], epilogue=L.EPI_GELU, want_pre=True)
-            z2 = _linear_fwd(g, w2, P["b2"], aux=h1)
+            if thr:
+                L.dropout(g, g, site_seed(drop[0], li, 2), thr)                           # dropout(GELU(.)), in place
+                z2 = _linear_fwd(g, w2, P["b2"])
+                L.dropout(z2, z2, site_seed(drop[0], li, 3), thr, residual=h1)          # h1 + dropout2(MLP block)
+            else:
+                z2 = _linear_fwd(g, w2, P["b2"], aux=h1)
             h2 = torch.empty_like(z2)
             mean2 = torch.empty_like(mean1)
             rstd2 = torch.empty_like(mean1)
@@ -120,6 +140,7 @@ class EncoderStackFn(torch.autograd.Function):
         ctx.saved_acts = saved
         ctx.params = params
         ctx.meta = (T, B, sep, nhead, precision, n_layers)
+        ctx.drop = drop if thr else None
         return h
 
     @staticmethod
@@ -147,32 +168,47 @@ class EncoderStackFn(torch.autograd.Function):
             ctx.saved_acts[li] = None
             in_w, out_w, w1, w2 = (_cast(P[k], dt) for k in ("in_w", "out_w", "w1", "w2"))
             # ---- LN2 and the MLP
+            drop = ctx.drop
             dz2 = torch.empty_like(z2)
-            L.layernorm_bwd(dh2, z2, mean2, rstd2, P["g2"], dz2, G["g2"], G["be2"], G["b2"])
+            L.layernorm_bwd(dh2, z2, mean2, rstd2, P["g2"], dz2, G["g2"], G["be2"], None if drop else G["b2"])
             del dh2, z2
-            _linear_wgrad(dz2, g, G["w2"])
-            du = _linear_dgrad(dz2, w2, aux=u, epilogue=L.EPI_GELU_BWD)
-            del g, u
+            dm = dz2
+            if drop:        # the MLP block saw dropout2: its output gradient is the masked, rescaled dz2 (residual keeps dz2)
+                dm = torch.empty_like(dz2)
+                L.dropout(dz2, dm, site_seed(drop[0], li, 3), drop[1])
+                L.colsum(dm, G["b2"])
+            _linear_wgrad(dm, g, G["w2"])
+            du = _linear_dgrad(dm, w2, aux=u, epilogue=L.EPI_GELU_BWD)
+            if drop:
+                L.dropout(du, du, site_seed(drop[0], li, 2), drop[1])       # mask of dropout(GELU(u)) commutes with GELU'(u)
+            del g, u, dm
             L.colsum(du, G["b1"])
             _linear_wgrad(du, h1, G["w1"])
             dh1 = _linear_dgrad(du, w1, aux=dz2)
             del du, dz2, h1
             # ---- LN1 and attention
             dz1 = torch.empty_like(z1)
-            L.layernorm_bwd(dh1, z1, mean1, rstd1, P["g1"], dz1, G["g1"], G["be1"], G["out_b"])
+            L.layernorm_bwd(dh1, z1, mean1, rstd1, P["g1"], dz1, G["g1"], G["be1"], None if drop else G["out_b"])
             del dh1, z1
-            _linear_wgrad(dz1, attn, G["out_w"])
-            dattn = _linear_dgrad(dz1, out_w)
+            da = dz1
+            if drop:
+                da = torch.empty_like(dz1)
+                L.dropout(dz1, da, site_seed(drop[0], li, 1), drop[1])
+                L.colsum(da, G["out_b"])
+            _linear_wgrad(da, attn, G["out_w"])
+            dattn = _linear_dgrad(da, out_w)
+            del da
             dqkv = torch.empty_like(qkv)
             delta = torch.empty_like(lse)
-            L.attention_bwd(qkv, attn, lse, dattn, dqkv, delta, T, B, nhead, dh, sep)
+            L.attention_bwd(qkv, attn, lse, dattn, dqkv, delta, T, B, nhead, dh, sep,
+                            drop=(site_seed(drop[0], li, 0), drop[1]) if drop else None)
             del dattn, attn, qkv
             L.colsum(dqkv, G["in_b"])
             _linear_wgrad(dqkv, h, G["in_w"])
             dh2 = _linear_dgrad(dqkv, in_w, aux=dz1)
             del dqkv, dz1, h
         ctx.saved_acts = None
-        return (dh2, None, None, None, None, None, None) + tuple(grads)
+        return (dh2, None, None, None, None, None, None, None) + tuple(grads)
 
 
 class EmbedFn(torch.autograd.Function):

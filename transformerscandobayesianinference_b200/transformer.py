@@ -10,6 +10,7 @@ import torch.nn as nn
 from torch.nn import TransformerEncoder, TransformerEncoderLayer
 
 from . import engine
+from ._lib import drop_threshold as L_drop_threshold
 from .positional_encodings import NoPositionalEncoding
 from .utils import SeqBN
 
@@ -85,8 +86,6 @@ class TransformerModel(nn.Module):
             raise RuntimeError(
                 "TransformerModel.forward runs on hand-written sm_100a kernels only; inputs are on "
                 f"{x_src.device}. Move model and data to a CUDA device (there is no CPU fallback).")
-        if self.training and self.dropout > 0:
-            raise NotImplementedError("dropout > 0 in training mode is not implemented by the sm_100a engine yet")
         T, B = x_src.shape[0], x_src.shape[1]
         sep = int(single_eval_pos)
         if sep < 0:                      # python slicing semantics of the reference (priors/omniglot.py:75 uses -1)
@@ -111,7 +110,12 @@ class TransformerModel(nn.Module):
         params = []
         for layer in self.transformer_encoder.layers:
             params.extend(engine.layer_params(layer))
-        h = engine.EncoderStackFn.apply(h, T, B, sep, self.nhead, precision, torch.is_grad_enabled(), *params)
+        drop = None
+        if self.training and self.dropout > 0:
+            # one seed per forward from torch's CPU generator (reproducible under torch.manual_seed, no device sync); the
+            # kernels derive per-layer / per-site counter-based masks from it
+            drop = (int(torch.randint(0, 2 ** 31 - 1, (1,)).item()), L_drop_threshold(self.dropout))
+        h = engine.EncoderStackFn.apply(h, T, B, sep, self.nhead, precision, torch.is_grad_enabled(), drop, *params)
 
         hq = h[sep * B:]
         if self._default_decoder():
