@@ -86,6 +86,10 @@ typedef struct pfn_attn_desc {
    * pfn_dropout_keep_mask's bit for (row = (b*H + h)*T + i, col = j) under drop_seed.  fp32-FMA kernels only. */
   uint32_t drop_seed;
   int drop_thr;
+  /* backward, tcgen05 kernels only, optional: dq_colsum[H*dh] += column sums of dQ (the q third of the in-projection bias
+   * gradient), accumulated from the staged dQ tiles so that dqkv need not be re-read.  (The k third is zero in exact
+   * arithmetic -- every row of dS sums to zero -- and the v third equals colsum(dO) = colsum(dz) W_out; see engine.py.) */
+  float* dq_colsum;
 } pfn_attn_desc;
 
 int pfn_attention_fwd_simt(const pfn_attn_desc* d, void* stream);

@@ -43,6 +43,7 @@ class AttnDesc(ctypes.Structure):
         ("dqkv", c_void_p), ("ld_dqkv", c_int),
         ("delta", c_void_p), ("batch_major", c_int),
         ("drop_seed", ctypes.c_uint32), ("drop_thr", c_int),
+        ("dq_colsum", c_void_p),
     ]
 
 
@@ -306,13 +307,18 @@ def attention_fwd(qkv, out, lse, T, B, H, dh, sep, use_tc=None, batch_major=Fals
 
 
 @_guarded
-def attention_bwd(qkv, out, lse, dout, dqkv, delta, T, B, H, dh, sep, use_tc=None, batch_major=False, drop=None):
+def attention_bwd(qkv, out, lse, dout, dqkv, delta, T, B, H, dh, sep, use_tc=None, batch_major=False, drop=None,
+                  dq_colsum=None):
+    """dq_colsum (fp32 [H*dh], tcgen05 path only): += column sums of dQ, taken from the staged tiles inside the kernel."""
     _count(2)
     lib = load()
-    require_cuda(qkv, out, lse, dout, dqkv, delta)
+    require_cuda(qkv, out, lse, dout, dqkv, delta, dq_colsum)
     d = attention_desc(qkv, out, lse, T, B, H, dh, sep, dout, dqkv, delta, batch_major=batch_major, drop=drop)
     if use_tc is None:
         use_tc = tc_attention_ok(qkv, dh) and not (drop and drop[1] > 0)
+    if dq_colsum is not None:
+        assert use_tc, "dq_colsum is produced by the tcgen05 backward only"
+        d.dq_colsum = dq_colsum.data_ptr()
     fn = lib.pfn_attention_bwd_tc if use_tc else lib.pfn_attention_bwd_simt
     check(fn(ctypes.byref(d), stream_ptr()), "pfn_attention_bwd")
 

@@ -24,6 +24,7 @@ struct AttnBwdParams {
   __nv_bfloat16* dqkv; int ld_dqkv;
   const float* lse;
   float* delta;
+  float* dq_colsum;      // optional [H*dh]: += column sums of dQ (dQ kernel epilogue)
   int n_tiles;
   int total_work;
   int batch_major;

@@ -643,7 +643,7 @@ extern "C" int pfn_attention_bwd_tc(const pfn_attn_desc* d, void* stream) {
   p.out = reinterpret_cast<const __nv_bfloat16*>(d->out); p.ld_out = d->ld_out;
   p.dout = reinterpret_cast<const __nv_bfloat16*>(d->dout); p.ld_dout = d->ld_dout;
   p.dqkv = reinterpret_cast<__nv_bfloat16*>(d->dqkv); p.ld_dqkv = d->ld_dqkv;
-  p.lse = d->lse; p.delta = d->delta;
+  p.lse = d->lse; p.delta = d->delta; p.dq_colsum = d->dq_colsum;
   p.batch_major = d->batch_major;
   p.trace = nullptr; p.trace_cap = g_trace_cap;
   static bool attr_set[64] = {};

@@ -21,6 +21,13 @@ N_LAYER_PARAMS = len(LAYER_PARAM_NAMES)
 LN_EPS = 1e-5
 
 
+# Data-parallel hook (parallel.OverlappedGradReducer): when set, it is called from inside the backward passes as soon as a
+# bucket of parameter gradients is complete in stream order -- `hook(flat_fp32_bucket)` -- so that its all-reduce overlaps the
+# rest of the backward; `GRAD_BUCKET_SYNC()` is called before the gradients are handed to autograd.
+GRAD_BUCKET_HOOK = None
+GRAD_BUCKET_SYNC = None
+
+
 def default_precision():
     return os.environ.get("PFN_B200_PRECISION", "bf16")
 
@@ -200,13 +207,28 @@ class EncoderStackFn(torch.autograd.Function):
             del da
             dqkv = torch.empty_like(qkv)
             delta = torch.empty_like(lse)
+            fused_bias = (not drop) and L.tc_attention_ok(qkv, dh)
             L.attention_bwd(qkv, attn, lse, dattn, dqkv, delta, T, B, nhead, dh, sep,
-                            drop=(site_seed(drop[0], li, 0), drop[1]) if drop else None)
+                            drop=(site_seed(drop[0], li, 0), drop[1]) if drop else None,
+                            dq_colsum=G["in_b"][:E] if fused_bias else None)
             del dattn, attn, qkv
-            L.colsum(dqkv, G["in_b"])
+            if fused_bias:
+                # in-projection bias gradient without re-reading dqkv (1.5 GB per layer at cfg 2): the q third comes out of
+                # the dQ kernel's staged tiles; the k third is zero in exact arithmetic (each row of dS sums to zero, so
+                # sum_j dK_j = sum_i (sum_j dS_ij) q_i = 0 -- the reference's value is rounding noise); the v third is
+                # sum_j dV_j = sum_i (sum_j P_ij) dO_i = colsum(dO) = colsum(dz1) W_out, and colsum(dz1) is the out_proj
+                # bias gradient the LayerNorm backward just produced.
+                G["in_b"][2 * E:] += G["out_b"] @ P["out_w"].detach().float()
+            else:
+                L.colsum(dqkv, G["in_b"])
             _linear_wgrad(dqkv, h, G["in_w"])
             dh2 = _linear_dgrad(dqkv, in_w, aux=dz1)
             del dqkv, dz1, h
+            if GRAD_BUCKET_HOOK is not None:       # this layer's 12 gradients are one contiguous slice of the flat buffer
+                lo = sum(sizes[:li * N_LAYER_PARAMS])
+                GRAD_BUCKET_HOOK(flat[lo:lo + sum(sizes[li * N_LAYER_PARAMS:(li + 1) * N_LAYER_PARAMS])])
+        if GRAD_BUCKET_SYNC is not None:
+            GRAD_BUCKET_SYNC()
         ctx.saved_acts = None
         return (dh2, None, None, None, None, None, None, None) + tuple(grads)
 
@@ -272,16 +294,21 @@ class DecoderFn(torch.autograd.Function):
         dl = torch.zeros(Nq, ld, device=dev, dtype=dt)
         dl[:, :n_out] = dlogits
         dlv = dl[:, :n_out]
-        dW2 = torch.zeros_like(W2, dtype=torch.float32)
-        db2 = torch.zeros(n_out, device=dev)
-        dW0 = torch.zeros_like(W0, dtype=torch.float32)
-        db0 = torch.zeros(W0.shape[0], device=dev)
+        sizes = [W0.numel(), W0.shape[0], W2.numel(), n_out]
+        flat = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)        # one bucket: a single all-reduce under DP
+        dW0 = flat[:sizes[0]].view(W0.shape)
+        db0 = flat[sizes[0]:sizes[0] + sizes[1]]
+        dW2 = flat[sizes[0] + sizes[1]:sizes[0] + sizes[1] + sizes[2]].view(W2.shape)
+        db2 = flat[sizes[0] + sizes[1] + sizes[2]:]
         L.colsum(dlv, db2)
         _linear_wgrad(dlv, g, dW2)
         du = _linear_dgrad(dlv, w2, aux=u, epilogue=L.EPI_GELU_BWD)
         L.colsum(du, db0)
         _linear_wgrad(du, hq, dW0)
         dhq = _linear_dgrad(du, w0)
+        if GRAD_BUCKET_HOOK is not None:
+            GRAD_BUCKET_HOOK(flat)
+            GRAD_BUCKET_SYNC()     # 2 MB bucket: wait for it (stream-level) so autograd never touches a buffer NCCL is still writing
         return dhq, dW0, db0, dW2, db2, None
 
 

@@ -72,6 +72,59 @@ def allreduce_gradients(params):
         g.copy_(synced)
 
 
+class OverlappedGradReducer:
+    """All-reduce of the gradient buckets the engine's backward reports (engine.GRAD_BUCKET_HOOK), overlapped with the rest of
+    the backward: every bucket (the decoder's four gradients; the twelve gradients of one encoder layer, last layer first) is
+    pre-divided by the world size and all-reduced IN PLACE on NCCL's stream as soon as it is complete in stream order; the
+    compute stream only waits for the outstanding collectives right before the gradients are handed to autograd.  Only the
+    few remaining parameters (input encoders) go through the plain end-of-step all-reduce.  Sum / world before clipping
+    reproduces the single-device gradient of the global-batch mean (reference train.py:92-97)."""
+
+    def __init__(self):
+        self.world = world_size()
+        self.handles = []
+        self.reduced_ptrs = set()
+        self.enabled = True
+
+    def install(self, engine_module):
+        engine_module.GRAD_BUCKET_HOOK = self.bucket_ready
+        engine_module.GRAD_BUCKET_SYNC = self.sync
+
+    def uninstall(self, engine_module):
+        engine_module.GRAD_BUCKET_HOOK = None
+        engine_module.GRAD_BUCKET_SYNC = None
+
+    def bucket_ready(self, flat):
+        if not self.enabled or self.world == 1:
+            return
+        flat.div_(self.world)
+        self.handles.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True))
+        self.reduced_ptrs.add((flat.data_ptr(), flat.numel()))
+
+    def sync(self):
+        for h in self.handles:
+            h.wait()                      # stream-level wait (the host does not block)
+        self.handles = []
+
+    def covers(self, grad):
+        """True if `grad` lives inside a bucket that was already all-reduced during this backward."""
+        p = grad.data_ptr()
+        return any(lo <= p < lo + 4 * n for lo, n in self.reduced_ptrs)
+
+    def finish(self, params):
+        """End of the backward: all-reduce whatever the buckets did not cover, then forget this step's buckets."""
+        self.sync()
+        if self.world > 1:
+            rest = [p.grad for p in params if p.grad is not None and not self.covers(p.grad)]
+            if rest:
+                flat = _flatten_dense_tensors(rest)
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+                flat.div_(self.world)
+                for g, synced in zip(rest, _unflatten_dense_tensors(flat, rest)):
+                    g.copy_(synced)
+        self.reduced_ptrs = set()
+
+
 def broadcast_object(obj, src=0):
     """Broadcast a small picklable python object (e.g. the epoch's single_eval_pos schedule)."""
     if world_size() == 1:

@@ -112,6 +112,9 @@ class Trainer:
         self.scheduler = scheduler(self.optimizer, warmup_epochs, epochs)
         self.params = [p for p in model.parameters() if p.requires_grad]
         self._micro = 0
+        # data parallel: bucketed all-reduce overlapped with the backward (one micro-batch per optimizer step); with gradient
+        # accumulation the accumulated buffer is reduced once at the end instead (reference semantics, train.py:92-97)
+        self.reducer = parallel.OverlappedGradReducer() if (world > 1 and on_cuda and aggregate_k_gradients == 1) else None
 
     # ------------------------------------------------------------------------------------------------------------
     def step(self, data, targets, single_eval_pos):
@@ -137,10 +140,21 @@ class Trainer:
         losses = losses.view(*output.shape[0:2]).squeeze(-1)
 
         loss = losses.mean()
-        loss.backward()
+        if self.reducer is not None:
+            from . import engine
+            self.reducer.install(engine)
+            try:
+                loss.backward()
+            finally:
+                self.reducer.uninstall(engine)
+        else:
+            loss.backward()
         self._micro += 1
         if self._micro % self.aggregate_k_gradients == 0:
-            parallel.allreduce_gradients(self.params)
+            if self.reducer is not None:
+                self.reducer.finish(self.params)
+            else:
+                parallel.allreduce_gradients(self.params)
             torch.nn.utils.clip_grad_norm_(model.parameters(), 1.)
             self.optimizer.step()
             self.optimizer.zero_grad()
