@@ -133,6 +133,9 @@ def trainer_args(name, cfg, batch, mods, device, n_steps):
     pk = dict(cfg["prior_kwargs"])
     pk["num_features"] = cfg["F"]
     pk["device"] = device
+    if "batch_size_per_gp_sample" in pk:          # bounded CPU samples use a smaller batch: keep the group size a divisor
+        import math
+        pk["batch_size_per_gp_sample"] = math.gcd(int(pk["batch_size_per_gp_sample"]), int(batch))
     if cfg["prior"] == "mlp":
         pk["hyperparameters"] = mlp_hyperparameters(priors.utils, torch.nn)
     prior_mod = getattr(priors, cfg["prior"])
