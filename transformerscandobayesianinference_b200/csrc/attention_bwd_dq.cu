@@ -435,12 +435,15 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
         // threads per column, 64 rows each -- instead of a separate pass re-reading dqkv from HBM
         const int tid = threadIdx.x - 64;                    // 0..255
         const int c = tid & 127, rh = tid >> 7;
-        const uint8_t* colp = sOut + (c >> 6) * 16384 + (c & 7) * 2;
+        const uint32_t colp = tc::smem_u32(sOut) + (c >> 6) * 16384 + (c & 7) * 2;   // explicit shared-space loads
         const int u = (c & 63) >> 3;
         float acc = 0.f;
 #pragma unroll 8
-        for (int r = rh * 64; r < rh * 64 + 64; ++r)
-          acc += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(colp + r * 128 + ((u ^ (r & 7)) << 4)));
+        for (int r = rh * 64; r < rh * 64 + 64; ++r) {
+          unsigned short bits;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(bits) : "r"(colp + r * 128 + ((u ^ (r & 7)) << 4)));
+          acc += __uint_as_float(static_cast<uint32_t>(bits) << 16);
+        }
         atomicAdd(p.dq_colsum + h * AB_DH + c, acc);
       }
       if (lane == 0) DQ_LOG(tr, 23 + 100 * warp, tcount, 0);      // epilogue end

@@ -52,8 +52,27 @@ struct GemmTcParams {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
-constexpr int kNumEpiWarps = 8;
+// Epilogue warps: a warp can only read its own quarter (32 lanes) of TMEM, so the unit is 4 warps = 128 rows.  Two column
+// halves x kEpiSub warps per (quarter, half): with kEpiSub = 2 every 32-column step of a half is split into two 16-column
+// pieces handled by different warps (16 epilogue warps = 4 per scheduler instead of 2).  Measured A/B on one B200
+// (tools/ab_lib.sh + tools/time_kernels.py, round 2): 16 warps change NOTHING for the GELU / GELU' shapes (0.730 / 0.810 ms
+// vs 0.725 / 0.811 ms) and cost the plain K = 512 shapes 2-3 % -- the epilogues are not latency-bound.  What bounds them is
+// shared-memory / L1 bandwidth: per 128 x 256 tile and 8 k-blocks a CTA moves 256 KB of operands in (TMA writes) and out
+// (tensor-core reads), 64 KB per staged output in and out again, plus the aux rows through L1 -- 640 KB per 4096 MMA clocks
+// for a plain tile (156 B/clk, the K = 512 shapes' ~80 % of peak), 768 KB with the second GELU output.  Default stays 8.
+#ifndef PFN_GEMM_EPI_WARPS
+#define PFN_GEMM_EPI_WARPS 8
+#endif
+constexpr int kNumEpiWarps = PFN_GEMM_EPI_WARPS;
+static_assert(kNumEpiWarps == 8 || kNumEpiWarps == 16, "8 or 16 epilogue warps");
+constexpr int kEpiSub = kNumEpiWarps / 8;        // warps per (TMEM lane quarter, column half)
+constexpr int kCW = 32 / kEpiSub;                // columns one thread handles per 32-column step
+constexpr int kGroupThreads = 128 * kEpiSub;     // threads that share one column half (and its staging buffer)
 constexpr int kNumThreads = 64 + kNumEpiWarps * 32;
+
+template <int N> struct TmemLd;
+template <> struct TmemLd<32> { static __device__ __forceinline__ void ld(uint32_t a, uint32_t (&v)[32]) { tc::tmem_ld_32x32b_x32(a, v); } };
+template <> struct TmemLd<16> { static __device__ __forceinline__ void ld(uint32_t a, uint32_t (&v)[16]) { tc::tmem_ld_32x32b_x16(a, v); } };
 
 template <int BLOCK_N, bool CTA2 = false>
 struct GemmCfg {
@@ -279,16 +298,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    // Two groups of four warps; group `half` owns the left / right BLOCK_N/2 columns of the tile and its own staging
-    // buffer ([128 rows x 64 cols] bf16 chunks in the TMA 128-byte swizzle).
+    // Two column halves; half `half` owns the left / right BLOCK_N/2 columns of the tile and its own staging buffer
+    // ([128 rows x 64 cols] bf16 chunks in the TMA 128-byte swizzle).  Within a half, warp `sub` of a lane quarter handles
+    // columns [sub * kCW, (sub + 1) * kCW) of every 32-column step.
     const int ew = warp - 2;
     const int q = warp & 3;              // TMEM lane quarter this warp may access
-    const int half = ew >> 2;            // column half
+    const int half = (ew >> 2) & 1;      // column half
+    const int sub = ew >> 3;             // which kCW-column piece of each 32-column step (0 when kEpiSub == 1)
     constexpr int COLS_PER_GROUP = BLOCK_N / 2;
     constexpr int OUT_CHUNKS = COLS_PER_GROUP / 64;
+    constexpr int NQ = kCW / 8;          // 16-byte units (8 bf16) per thread and step
     uint8_t* stg = sOut + half * (Cfg::kStageOutBytes / 2);
-    const bool issuer = (ew & 3) == 0 && lane == 0;       // the one thread per group that owns the bulk-store groups
-    const int nbar = 1 + half;                             // named barrier of this group (0 is __syncthreads)
+    const bool issuer = (ew & 3) == 0 && sub == 0 && lane == 0;   // the one thread per half that owns the bulk-store groups
+    const int nbar = 1 + half;                             // named barrier of this half (0 is __syncthreads)
     // GELU with a second (pre-activation) output: BLOCK_N = 256 tiles run ONE pass over the accumulator in two rounds of 64
     // columns, staging u in chunk slot 0 and GELU(u) in slot 1 (two bulk stores per round); the narrow tile keeps two passes.
     const bool gelu_c2 = p.tma_store && p.act == PFN_EPI_GELU && p.C2 != nullptr;
@@ -310,24 +332,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool row_ok = row < p.M;
       const bool add_bias = p.bias != nullptr && split == 0;
       const bool aux_now = use_aux && row_ok && (p.act == PFN_EPI_GELU_BWD || split == 0);
-      const int gcol0 = n0 + half * COLS_PER_GROUP;          // first column of this group
-      // Software pipeline: the aux (residual / pre-activation) row segment and the TMEM chunk of step c+1 are requested
+      const int gcol0 = n0 + half * COLS_PER_GROUP + sub * kCW;          // first column this THREAD handles (step 0)
+      // Software pipeline: the aux (residual / pre-activation) row segment and the TMEM piece of step c+1 are requested
       // before step c is computed; the very first aux request goes out before the accumulator is even complete.
-      uint4 aq[4];                // aux of the next chunk (two chunks ahead measured slower: tools/ab_gemm.py)
-      auto aux_request = [&](int cc, uint4 (&dst)[4]) {
+      uint4 aq[NQ];               // aux of the next step (two steps ahead measured slower: tools/ab_gemm.py)
+      auto aux_request = [&](int cc, uint4 (&dst)[NQ]) {
         const __nv_bfloat16* src = p.aux + static_cast<size_t>(row) * p.ld_aux + gcol0 + cc;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) dst[i] = __ldg(reinterpret_cast<const uint4*>(src) + i);
+        for (int i = 0; i < NQ; ++i) dst[i] = __ldg(reinterpret_cast<const uint4*>(src) + i);
       };
-      auto aux_fast = [&](int cc) { return aux_now && gcol0 + cc + 32 <= p.N; };
+      auto aux_fast = [&](int cc) { return aux_now && gcol0 + cc + kCW <= p.N; };
       if (aux_fast(0)) aux_request(0, aq);
       if (use_aux && w + work_stride < total_work) {
-        // pull the NEXT tile's aux row segment (COLS_PER_GROUP bf16 = 128 / 256 B) towards L2 while this tile is processed
+        // pull the NEXT tile's aux row segment (this thread's share of COLS_PER_GROUP bf16) towards L2 while this tile is processed
         const int w2 = w + work_stride;
         const int tile2 = w2 - (w2 / tiles) * tiles;
         const int row2 = (tile2 / p.tiles_n) * kTileM + static_cast<int>(cta_rank) * kBlockM + trow;
         const int col2 = (tile2 % p.tiles_n) * BLOCK_N + half * COLS_PER_GROUP;
-        if (row2 < p.M && col2 < p.N) {
+        if (row2 < p.M && col2 < p.N && sub == 0) {
           const char* pa = reinterpret_cast<const char*>(p.aux + static_cast<size_t>(row2) * p.ld_aux + col2);
 #pragma unroll
           for (int o = 0; o < COLS_PER_GROUP * 2; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + o));
@@ -336,7 +358,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (p.stall != nullptr) { const long long t0 = clock64(); tc::mbar_wait(&tfull_bar[as], aphase); st_tfull += clock64() - t0; }
       else tc::mbar_wait(&tfull_bar[as], aphase);
       tc::tc_fence_after();
-      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BLOCK_N + half * COLS_PER_GROUP);
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                             static_cast<uint32_t>(as * BLOCK_N + half * COLS_PER_GROUP + sub * kCW);
       const int npass = (dual || two_pass) ? 2 : 1;
 #pragma unroll 1
       for (int pass = 0; pass < npass; ++pass) {
@@ -348,13 +371,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // the previous bulk store must have finished READING the staging buffer before it is overwritten
           const long long t0 = p.stall != nullptr ? clock64() : 0;
           if (issuer) tc::tma_store_wait_read<0>();
-          asm volatile("bar.sync %0, 128;" ::"r"(nbar) : "memory");
+          asm volatile("bar.sync %0, %1;" ::"r"(nbar), "n"(kGroupThreads) : "memory");
           if (p.stall != nullptr) st_stage += clock64() - t0;
           store_pending = false;
         }
         const long long tc0 = p.stall != nullptr ? clock64() : 0;
-        uint32_t v[32];
-        if (gcol0 + cc_begin < p.N) tc::tmem_ld_32x32b_x32(tbase + cc_begin, v);
+        uint32_t v[kCW];
+        if (gcol0 + cc_begin < p.N) TmemLd<kCW>::ld(tbase + cc_begin, v);
         if (pass > 0) {           // (aux never accompanies a second pass today; kept correct)
           if (aux_fast(cc_begin)) aux_request(cc_begin, aq);
         }
@@ -364,37 +387,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (col0 >= p.N) break;  // warp-uniform
           if (p.stall != nullptr) { const long long t0 = clock64(); tc::tmem_ld_wait(); st_ldw += clock64() - t0; }
           else tc::tmem_ld_wait();
-          float f[32];
+          float f[kCW];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          for (int i = 0; i < kCW; ++i) f[i] = __uint_as_float(v[i]);
           const bool have_aux = aux_fast(cc);
-          uint4 ac[4];
+          uint4 ac[NQ];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) ac[i] = aq[i];
+          for (int i = 0; i < NQ; ++i) ac[i] = aq[i];
           if (cc + 32 < cc_end && col0 + 32 < p.N)
-            tc::tmem_ld_32x32b_x32(tbase + cc + 32, v);               // in flight while this chunk is computed
+            TmemLd<kCW>::ld(tbase + cc + 32, v);               // in flight while this step is computed
           if (cc + 32 < cc_end && aux_fast(cc + 32)) aux_request(cc + 32, aq);
-          const bool full_chunk = (col0 + 32 <= p.N);
+          const bool full_chunk = (col0 + kCW <= p.N);
           if (add_bias) {
             if (full_chunk) {
 #pragma unroll
-              for (int i = 0; i < 32; i += 4) {
+              for (int i = 0; i < kCW; i += 4) {
                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
                 f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
               }
             } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
+              for (int i = 0; i < kCW; ++i)
                 if (col0 + i < p.N) f[i] += __ldg(p.bias + col0 + i);
             }
           }
+          // 16-byte unit (8 bf16) index of this thread's first column inside its 64-column staging chunk
+          const int u0 = ((cc & 63) >> 3) + sub * NQ;
           if (p.act == PFN_EPI_GELU && !write_pre_only) {
             if (dual) {
               // pre-activation goes to chunk slot 0 of the staging buffer (same swizzle as the main output below)
               uint8_t* rowp = stg + trow * 128;
-              const int u0 = (cc & 63) >> 3;
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
+              for (int i = 0; i < NQ; ++i) {
                 uint4 pk;
                 pk.x = tc::pack_bf16x2(f[8 * i], f[8 * i + 1]); pk.y = tc::pack_bf16x2(f[8 * i + 2], f[8 * i + 3]);
                 pk.z = tc::pack_bf16x2(f[8 * i + 4], f[8 * i + 5]); pk.w = tc::pack_bf16x2(f[8 * i + 6], f[8 * i + 7]);
@@ -404,7 +428,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               __nv_bfloat16* dst = p.C2 + static_cast<size_t>(row) * p.ldc2 + col0;
               if (full_chunk) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 8) {
+                for (int i = 0; i < kCW; i += 8) {
                   uint4 pk;
                   pk.x = tc::pack_bf16x2(f[i], f[i + 1]); pk.y = tc::pack_bf16x2(f[i + 2], f[i + 3]);
                   pk.z = tc::pack_bf16x2(f[i + 4], f[i + 5]); pk.w = tc::pack_bf16x2(f[i + 6], f[i + 7]);
@@ -412,57 +436,56 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
               } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
+                for (int i = 0; i < kCW; ++i)
                   if (col0 + i < p.N) dst[i] = __float2bfloat16_rn(f[i]);
               }
             }
 #ifdef PFN_GELU_TANH_F16X2
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) gelu_fast2(f[i], f[i + 1]);
+            for (int i = 0; i < kCW; i += 2) gelu_fast2(f[i], f[i + 1]);
 #else
 #pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = gelu_fast(f[i]);
+            for (int i = 0; i < kCW; ++i) f[i] = gelu_fast(f[i]);
 #endif
           }
           if (aux_now && !write_pre_only) {
-            float a[32];
+            float a[kCW];
             if (have_aux) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
+              for (int i = 0; i < NQ; ++i) {
                 const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&ac[i]);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 t = __bfloat1622float2(h[j]);
-                  a[8 * i + 2 * j] = t.x; a[8 * i + 2 * j + 1] = t.y;
+                for (int jj = 0; jj < 4; ++jj) {
+                  const float2 t = __bfloat1622float2(h[jj]);
+                  a[8 * i + 2 * jj] = t.x; a[8 * i + 2 * jj + 1] = t.y;
                 }
               }
             } else {
               const __nv_bfloat16* src = p.aux + static_cast<size_t>(row) * p.ld_aux + col0;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) a[i] = (col0 + i < p.N) ? __bfloat162float(src[i]) : 0.f;
+              for (int i = 0; i < kCW; ++i) a[i] = (col0 + i < p.N) ? __bfloat162float(src[i]) : 0.f;
             }
             if (p.act == PFN_EPI_GELU_BWD) {
 #ifdef PFN_GELU_TANH_F16X2
 #pragma unroll
-              for (int i = 0; i < 32; i += 2) {
+              for (int i = 0; i < kCW; i += 2) {
                 gelu_grad_fast2(a[i], a[i + 1]);
                 f[i] *= a[i]; f[i + 1] *= a[i + 1];
               }
 #else
 #pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] *= gelu_grad_fast(a[i]);
+              for (int i = 0; i < kCW; ++i) f[i] *= gelu_grad_fast(a[i]);
 #endif
             } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] += a[i];
+              for (int i = 0; i < kCW; ++i) f[i] += a[i];
             }
           }
           if (p.tma_store) {
-            // staging write: 64-column chunk (cc / 64), 16-byte units (cc % 64) / 8 .. +3 of row `trow`, XOR-swizzled
+            // staging write: 64-column chunk (cc / 64), 16-byte units u0 .. u0 + NQ - 1 of row `trow`, XOR-swizzled
             uint8_t* rowp = stg + (dual ? 1 : (cc >> 6)) * 16384 + trow * 128;
-            const int u0 = (cc & 63) >> 3;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < NQ; ++i) {
               uint4 pk;
               pk.x = tc::pack_bf16x2(f[8 * i], f[8 * i + 1]); pk.y = tc::pack_bf16x2(f[8 * i + 2], f[8 * i + 3]);
               pk.z = tc::pack_bf16x2(f[8 * i + 4], f[8 * i + 5]); pk.w = tc::pack_bf16x2(f[8 * i + 6], f[8 * i + 7]);
@@ -473,22 +496,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               float* dst = reinterpret_cast<float*>(p.C) + static_cast<size_t>(row) * p.ldc + col0;
               if (p.accumulate) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
+                for (int i = 0; i < kCW; ++i)
                   if (col0 + i < p.N) atomicAdd(dst + i, f[i]);
               } else if (full_chunk) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 4)
+                for (int i = 0; i < kCW; i += 4)
                   *reinterpret_cast<float4*>(dst + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
               } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
+                for (int i = 0; i < kCW; ++i)
                   if (col0 + i < p.N) dst[i] = f[i];
               }
             } else {
               __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<size_t>(row) * p.ldc + col0;
               if (full_chunk) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 8) {
+                for (int i = 0; i < kCW; i += 8) {
                   uint4 pk;
                   pk.x = tc::pack_bf16x2(f[i], f[i + 1]); pk.y = tc::pack_bf16x2(f[i + 2], f[i + 3]);
                   pk.z = tc::pack_bf16x2(f[i + 4], f[i + 5]); pk.w = tc::pack_bf16x2(f[i + 6], f[i + 7]);
@@ -496,7 +519,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
               } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
+                for (int i = 0; i < kCW; ++i)
                   if (col0 + i < p.N) dst[i] = __float2bfloat16_rn(f[i]);
               }
             }
@@ -511,10 +534,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (p.tma_store) {
           tc::fence_proxy_async_smem();                       // generic-proxy staging writes -> visible to the TMA
-          asm volatile("bar.sync %0, 128;" ::"r"(nbar) : "memory");
+          asm volatile("bar.sync %0, %1;" ::"r"(nbar), "n"(kGroupThreads) : "memory");
           if (issuer) {
+            const int hcol0 = n0 + half * COLS_PER_GROUP;      // first column of this half
             if (dual) {
-              const int cbase = gcol0 + pass * 64;
+              const int cbase = hcol0 + pass * 64;
               if (cbase < p.N) {
                 tc::tma_store_2d(&tmC2, stg, cbase, m0);
                 tc::tma_store_2d(&tmC, stg + 16384, cbase, m0);
@@ -523,7 +547,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const CUtensorMap* tm = write_pre_only ? &tmC2 : &tmC;
 #pragma unroll
               for (int c = 0; c < OUT_CHUNKS; ++c) {
-                const int cbase = gcol0 + c * 64;
+                const int cbase = hcol0 + c * 64;
                 if (cbase < p.N) tc::tma_store_2d(tm, stg + c * 16384, cbase, m0);   // rows >= M / cols >= N are clipped
               }
             }

@@ -142,7 +142,9 @@ class EncoderStackFn(torch.autograd.Function):
             rstd2 = torch.empty_like(mean1)
             L.layernorm_fwd(z2, P["g2"], P["be2"], h2, mean2, rstd2, LN_EPS)
             if keep:
-                saved.append((h, qkv, attn, lse, z1, mean1, rstd1, h1, u, g, z2, mean2, rstd2))
+                # the activation-dtype weight copies are kept for the backward as well (4 small tensors per layer) instead of
+                # being cast a second time there
+                saved.append((h, qkv, attn, lse, z1, mean1, rstd1, h1, u, g, z2, mean2, rstd2, in_w, out_w, w1, w2))
             h = h2
         ctx.saved_acts = saved
         ctx.params = params
@@ -171,9 +173,8 @@ class EncoderStackFn(torch.autograd.Function):
         for li in reversed(range(n_layers)):
             P = dict(zip(LAYER_PARAM_NAMES, params[li * N_LAYER_PARAMS:(li + 1) * N_LAYER_PARAMS]))
             G = dict(zip(LAYER_PARAM_NAMES, grads[li * N_LAYER_PARAMS:(li + 1) * N_LAYER_PARAMS]))
-            h, qkv, attn, lse, z1, mean1, rstd1, h1, u, g, z2, mean2, rstd2 = ctx.saved_acts[li]
+            h, qkv, attn, lse, z1, mean1, rstd1, h1, u, g, z2, mean2, rstd2, in_w, out_w, w1, w2 = ctx.saved_acts[li]
             ctx.saved_acts[li] = None
-            in_w, out_w, w1, w2 = (_cast(P[k], dt) for k in ("in_w", "out_w", "w1", "w2"))
             # ---- LN2 and the MLP
             drop = ctx.drop
             dz2 = torch.empty_like(z2)
@@ -279,17 +280,16 @@ class DecoderFn(torch.autograd.Function):
         logits_buf = torch.empty(hq.shape[0], ld, device=hq.device, dtype=torch.float32)
         logits = logits_buf[:, :n_out]
         L.gemm(g, w2, logits, bias=b2.detach().contiguous())
-        ctx.save_for_backward(hq, u, g, W0, W2)
+        ctx.save_for_backward(hq, u, g, W0, W2, w0, w2)
         ctx.precision = precision
         return logits
 
     @staticmethod
     def backward(ctx, dlogits):
-        hq, u, g, W0, W2 = ctx.saved_tensors
+        hq, u, g, W0, W2, w0, w2 = ctx.saved_tensors
         dt = act_dtype(ctx.precision)
         dev = dlogits.device
         Nq, n_out = dlogits.shape
-        w0, w2 = _cast(W0, dt), _cast(W2, dt)
         ld = (n_out + 7) // 8 * 8
         dl = torch.zeros(Nq, ld, device=dev, dtype=dt)
         dl[:, :n_out] = dlogits
