@@ -83,7 +83,7 @@ typedef struct pfn_attn_desc {
   int batch_major;         /* 0: token row = t*B + b (reference layout); 1: token row = b*T + t (tcgen05 kernels only) */
   /* dropout on the attention probabilities (torch:nn/functional.py multi_head_attention_forward `dropout_p`; reference
    * train.py:22 default 0.2): drop_thr = round(256 p) in [0,255], 0 = off; the keep bit of (row i, key j) of head (b,h) is
-   * pfn_dropout_keep_mask's bit for (row = (b*H + h)*T + i, col = j) under drop_seed.  fp32-FMA kernels only. */
+   * pfn_dropout_keep_mask's bit for (row = (b*H + h)*T + i, col = j) under drop_seed. */
   uint32_t drop_seed;
   int drop_thr;
   /* backward, tcgen05 kernels only, optional: dq_colsum[H*dh] += column sums of dQ (the q third of the in-projection bias

@@ -218,3 +218,30 @@ def test_one_factor_exact_gp_predictive_identity():
     mse = ((d * alpha) ** 2)[:, 1:].transpose(0, 1)
     assert torch.allclose(nll, O.gp_exact_predictive_ref(x, y, ls, os_, noise), rtol=1e-9, atol=1e-9)
     assert torch.allclose(mse, O.gp_exact_predictive_ref(x, y, ls, os_, noise, use_mse=True), rtol=1e-8, atol=1e-10)
+
+
+def test_gp_kernel_oracle_known_answers():
+    """The GP parts of the oracle cannot be pinned against gpytorch (not installed, no reference vectors): pin them against the
+    PUBLISHED closed forms instead (Rasmussen & Williams, GPML: squared exponential eq. 4.9; Matern nu = 1/2, 3/2, 5/2
+    eq. 4.14-4.17 -- the formulas gpytorch.kernels.RBFKernel / MaternKernel implement), at hand-computed points, plus the
+    semantics the reference relies on: noise on the diagonal only (GaussianLikelihood), outputscale multiplies the kernel
+    (ScaleKernel), per-dimension lengthscales divide the inputs (ARD), and psd_safe_cholesky's jitter ladder 1e-6, 1e-5, 1e-4."""
+    import math
+    from oracle import pfn_oracle as O
+    from transformerscandobayesianinference_b200.priors import fast_gp
+    x = torch.tensor([[[0.0, 0.0], [1.0, 0.0], [0.0, 2.0]]], dtype=torch.float64)         # one dataset, 3 points, 2 dims
+    one = torch.ones(1, dtype=torch.float64)
+    ls1 = torch.ones(1, 2, dtype=torch.float64)
+    want = {"rbf": math.exp(-0.5), "matern12": math.exp(-1.0), "matern32": (1 + math.sqrt(3)) * math.exp(-math.sqrt(3)),
+            "matern52": (1 + math.sqrt(5) + 5.0 / 3.0) * math.exp(-math.sqrt(5))}
+    known = {"rbf": 0.60653066, "matern12": 0.36787944, "matern32": 0.48335772, "matern52": 0.52399411}   # 8 significant digits
+    for name, v in want.items():
+        assert abs(v - known[name]) < 1e-8
+        K = O.gp_kernel_ref(x, ls1, 3.0 * one, 0.25 * one, kernel=name)[0]
+        assert abs(K[0, 1].item() - 3.0 * v) < 1e-12                         # unit distance, outputscale 3
+        assert abs(K[0, 0].item() - (3.0 + 0.25)) < 1e-12                    # k(x,x) = 1, noise on the diagonal only
+        assert abs(K[1, 0].item() - K[0, 1].item()) < 1e-15
+    # ARD: distance 2 along a dimension with lengthscale 2 is a unit distance again
+    K = O.gp_kernel_ref(x, torch.tensor([[1.0, 2.0]], dtype=torch.float64), one, 0 * one, kernel="rbf")[0]
+    assert abs(K[0, 2].item() - math.exp(-0.5)) < 1e-12 and abs(K[1, 2].item() - math.exp(-1.0)) < 1e-12
+    assert fast_gp._JITTERS == (0.0, 1e-6, 1e-5, 1e-4)

@@ -295,13 +295,13 @@ def tc_attention_ok(qkv, dh, T=None):
 
 @_guarded
 def attention_fwd(qkv, out, lse, T, B, H, dh, sep, use_tc=None, batch_major=False, drop=None):
-    """drop = (seed, thr): dropout on the attention probabilities (fp32-FMA kernels only; thr 0 / None = off)."""
+    """drop = (seed, thr): dropout on the attention probabilities (thr 0 / None = off)."""
     _count(1)
     lib = load()
     require_cuda(qkv, out, lse)
     d = attention_desc(qkv, out, lse, T, B, H, dh, sep, batch_major=batch_major, drop=drop)
     if use_tc is None:
-        use_tc = tc_attention_ok(qkv, dh) and not (drop and drop[1] > 0)
+        use_tc = tc_attention_ok(qkv, dh)
     fn = lib.pfn_attention_fwd_tc if use_tc else lib.pfn_attention_fwd_simt
     check(fn(ctypes.byref(d), stream_ptr()), "pfn_attention_fwd")
 
@@ -315,7 +315,7 @@ def attention_bwd(qkv, out, lse, dout, dqkv, delta, T, B, H, dh, sep, use_tc=Non
     require_cuda(qkv, out, lse, dout, dqkv, delta, dq_colsum)
     d = attention_desc(qkv, out, lse, T, B, H, dh, sep, dout, dqkv, delta, batch_major=batch_major, drop=drop)
     if use_tc is None:
-        use_tc = tc_attention_ok(qkv, dh) and not (drop and drop[1] > 0)
+        use_tc = tc_attention_ok(qkv, dh)
     if dq_colsum is not None:
         assert use_tc, "dq_colsum is produced by the tcgen05 backward only"
         d.dq_colsum = dq_colsum.data_ptr()

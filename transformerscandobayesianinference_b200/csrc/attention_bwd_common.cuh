@@ -25,6 +25,7 @@ struct AttnBwdParams {
   const float* lse;
   float* delta;
   float* dq_colsum;      // optional [H*dh]: += column sums of dQ (dQ kernel epilogue)
+  uint32_t drop_seed; int drop_thr;   // dropout on the attention probabilities (thr 0 = off), csrc/dropout.cuh
   int n_tiles;
   int total_work;
   int batch_major;

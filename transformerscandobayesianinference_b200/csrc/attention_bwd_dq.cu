@@ -25,6 +25,7 @@
 // dS_j (packed bf16) aliases its own S buffer: keys 0..31 -> columns +0..15, keys 32..63 -> columns +32..47 (each half is
 // written by the warps that read exactly those score columns, so no thread overwrites scores another thread still needs).
 #include "attention_bwd_common.cuh"
+#include "dropout.cuh"
 
 #ifdef PFN_DQ_TRACE
 #define DQ_LOG(tr, ...) (tr).log(__VA_ARGS__)
@@ -324,7 +325,27 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
         tc::tmem_ld_32x32b_x32(tmem_base + lane_off + TM_S + buf * 64 + half * 32, s);
         tc::tmem_ld_32x32b_x32(tmem_base + lane_off + TM_DP + buf * 64 + half * 32, dp);
         tc::tmem_ld_wait();
-        if (!diag && kmax >= 64) {
+        if (!diag && p.drop_thr > 0) {
+          // dropout on the probabilities (csrc/dropout.cuh): dS = P (m dP / (1 - p) - delta) scale, keep bit of key j = byte j & 3
+          // of the hash of (row id (b*H + h)*T + i, j >> 2); covers full and partial dense blocks
+          const float dsc = drop_scale(p.drop_thr);
+          const uint32_t rid = static_cast<uint32_t>(bh) * p.T + i;
+          const int kb = (j - nd) * 64 + half * 32;           // first key of this thread's 32 columns
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const uint32_t hsh = drop_hash(p.drop_seed, rid, static_cast<uint32_t>(kb >> 2) + q4);
+            float dv4[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int c = 4 * q4 + e;
+              const float mk = drop_keep_byte(hsh, e, p.drop_thr) ? dsc : 0.f;
+              const float pr = tc::fast_exp2(fmaf(__uint_as_float(s[c]), p.scale_log2, -lse2));
+              dv4[e] = (half * 32 + c < kmax) ? pr * fmaf(__uint_as_float(dp[c]) * mk, p.scale, -dls) : 0.f;
+            }
+            pk[2 * q4] = tc::pack_bf16x2(dv4[0], dv4[1]);
+            pk[2 * q4 + 1] = tc::pack_bf16x2(dv4[2], dv4[3]);
+          }
+        } else         if (!diag && kmax >= 64) {
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
             const float p0 = tc::fast_exp2(fmaf(__uint_as_float(s[2 * c]), p.scale_log2, -lse2));
@@ -360,7 +381,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
             // the diagonal key is attended by this row only: dK_i = dS_ii q_i and dV_i = P_ii dO_i are complete.
             // Q / dO rows are read back from the (still live) swizzled smem tiles.
             const float pii = tc::fast_exp2(fmaf(sv, p.scale_log2, -lse2));
-            dself = pii * fmaf(dv, p.scale, -dls);
+            float mk = 1.f;                                 // dropout keep factor of the diagonal key (column i of row i)
+            if (p.drop_thr > 0) mk = drop_keep(p.drop_seed, static_cast<uint32_t>(bh) * p.T + i, static_cast<uint32_t>(i), p.drop_thr) ? drop_scale(p.drop_thr) : 0.f;
+            dself = pii * fmaf(dv * mk, p.scale, -dls);
             const size_t tokq = p.batch_major ? static_cast<size_t>(b) * p.T + i : static_cast<size_t>(i) * p.B + b;
             __nv_bfloat16* dkv_out = p.dqkv + tokq * p.ld_dqkv + h * AB_DH;
 #pragma unroll 1
@@ -369,7 +392,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
               ab_load32_swz(sQ, row, c * 32, qq);
               ab_load32_swz(sDO, row, c * 32, dd);
 #pragma unroll
-              for (int e = 0; e < 32; ++e) { qq[e] *= dself; dd[e] *= pii; }
+              for (int e = 0; e < 32; ++e) { qq[e] *= dself; dd[e] *= pii * mk; }
               ab_store32(dkv_out + E + c * 32, qq);
               ab_store32(dkv_out + 2 * E + c * 32, dd);
             }

@@ -2,7 +2,7 @@
 //
 //  (0) attn_bwd_delta_kernel   delta[b,h,i] = dO_i . O_i   (one warp per token row, HBM-bound, 16 B vectors)
 //
-//  (1) attn_bwd_dq_tc_kernel   one CTA per (batch, head, 128-row query tile); blocks = 64-key blocks of the train keys
+//  (1) attn_bwd_dq_tc_kernel   [attention_bwd_dq.cu] one CTA per (batch, head, 128-row query tile); blocks = 64-key blocks of the train keys
 //      followed by up to two "diagonal" blocks (the tile's own rows as keys; row i keeps only key i, cf. attention_tc.cu):
 //          S_j  = Q K_j^T          dP_j = dO V_j^T                      (SS MMAs, 128x64x128, TMEM double-buffered)
 //          dS_j = exp2(S_j c - lse) * (dP_j - delta) * scale   -> bf16 -> TMEM   (one thread per query row)
@@ -22,6 +22,7 @@
 #include <stdlib.h>
 
 #include "attention_bwd_common.cuh"
+#include "dropout.cuh"
 
 namespace pfn {
 
@@ -62,294 +63,6 @@ attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ out, int ld_out, const _
       for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
       if ((lane & 15) == 0 && h < H) delta[(static_cast<size_t>(b) * H + h) * T + t] = acc;
     }
-  }
-}
-
-// =====================================================================================================================
-// Kernel 1: dQ (+ diagonal-key dK/dV of query rows)
-// =====================================================================================================================
-__global__ void __launch_bounds__(AB_THREADS, 1)
-attn_bwd_dq_v1_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
-                      const __grid_constant__ CUtensorMap tmDO128, const AttnBwdParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sDO = smem + AB_TILE_BYTES;
-  uint8_t* sKV = smem + 2 * AB_TILE_BYTES;               // stage s: K at +s*32K, V at +16K
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * AB_TILE_BYTES + AB_KS * 2 * AB_BLK_BYTES + 1024);
-  uint64_t* qdo_full = bars + 0;
-  uint64_t* qdo_empty = bars + 1;   // MMA commit after the tile's last score MMA + one arrival per row thread
-  uint64_t* kv_full = bars + 2;                  // [AB_KS]
-  uint64_t* kv_empty = bars + 2 + AB_KS;         // [AB_KS]
-  uint64_t* s_full = bars + 2 + 2 * AB_KS;       // [3]
-  uint64_t* ds_ready = s_full + 3;               // [3]
-  uint64_t* dq_done = s_full + 6;
-  uint64_t* dq_empty = s_full + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 8);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int E = p.H * AB_DH;
-
-  if (warp == 0 && lane == 0) {
-    tc::tma_prefetch_desc(&tmQKV128);
-    tc::tma_prefetch_desc(&tmQKV64);
-    tc::tma_prefetch_desc(&tmDO128);
-  }
-  if (warp == 1 && lane == 0) {
-    tc::mbar_init(qdo_full, 1);
-    tc::mbar_init(qdo_empty, 1 + AB_EW_WARPS);   // MMA commit (score MMAs done) + every row thread (smem row reads done)
-    for (int s = 0; s < AB_KS; ++s) {
-      tc::mbar_init(&kv_full[s], 1);
-      tc::mbar_init(&kv_empty[s], 1);
-    }
-    for (int s = 0; s < 3; ++s) {
-      tc::mbar_init(&s_full[s], 1);
-      tc::mbar_init(&ds_ready[s], AB_EW_WARPS);
-    }
-    tc::mbar_init(dq_done, 1);
-    tc::mbar_init(dq_empty, AB_EW_WARPS);
-    tc::mbar_fence_init();
-  }
-  if (warp == 2) {
-    tc::tmem_alloc(tmem_slot, 512);
-    tc::tmem_relinquish();
-  }
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const int nblk = (p.sep + 63) / 64;
-  // TMEM columns: S[3] @0,64,128 | dP[3] @192,256,320 | dQ @384..511   (three score blocks in flight)
-
-  if (warp == 0) {
-    {
-      tc::KernelTrace tr = tc::trace_make(p.trace, p.trace_cap, 0);
-      uint32_t g = 0, tcount = 0;
-      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
-        const int bh = w / p.n_tiles;
-        const int qt = w - bh * p.n_tiles;
-        const int b = bh / p.H, h = bh - b * p.H;
-        const int i0 = qt * 128;
-        int dstart[2];
-        const int nb = ab_tile_block_plan(i0, p.sep, p.T, nblk, dstart);
-        tc::mbar_wait(qdo_empty, (tcount & 1) ^ 1);
-        if (lane == 0) tr.log(1, tcount, 0);
-        if (tc::elect_one()) {
-          tc::mbar_expect_tx(qdo_full, 2 * AB_TILE_BYTES);
-          tc::tma_load_3d(sQ, &tmQKV128, qdo_full, h * AB_DH, b, i0);
-          tc::tma_load_3d(sQ + 16384, &tmQKV128, qdo_full, h * AB_DH + 64, b, i0);
-          tc::tma_load_3d(sDO, &tmDO128, qdo_full, h * AB_DH, b, i0);
-          tc::tma_load_3d(sDO + 16384, &tmDO128, qdo_full, h * AB_DH + 64, b, i0);
-        }
-        __syncwarp();
-        for (int j = 0; j < nb; ++j, ++g) {
-          const int st = g % AB_KS;
-          tc::mbar_wait(&kv_empty[st], ((g / AB_KS) & 1) ^ 1);
-          if (lane == 0) tr.log(2, tcount, j);
-          uint8_t* kdst = sKV + st * 2 * AB_BLK_BYTES;
-          uint8_t* vdst = kdst + AB_BLK_BYTES;
-          const int j0 = j < nblk ? j * 64 : dstart[j - nblk];
-          if (tc::elect_one()) {
-            tc::mbar_expect_tx(&kv_full[st], 2 * AB_BLK_BYTES);
-            tc::tma_load_3d(kdst, &tmQKV64, &kv_full[st], E + h * AB_DH, b, j0);
-            tc::tma_load_3d(kdst + 8192, &tmQKV64, &kv_full[st], E + h * AB_DH + 64, b, j0);
-            tc::tma_load_3d(vdst, &tmQKV64, &kv_full[st], 2 * E + h * AB_DH, b, j0);
-            tc::tma_load_3d(vdst + 8192, &tmQKV64, &kv_full[st], 2 * E + h * AB_DH + 64, b, j0);
-          }
-          __syncwarp();
-        }
-      }
-    }
-  } else if (warp == 1) {
-    {
-      tc::KernelTrace tr = tc::trace_make(p.trace, p.trace_cap, 1);
-      uint32_t g = 0, tcount = 0;
-      const uint32_t q_addr = tc::smem_u32(sQ), do_addr = tc::smem_u32(sDO);
-      auto issue_scores = [&](uint32_t gg) {
-        const uint32_t k_addr = tc::smem_u32(sKV + (gg % AB_KS) * 2 * AB_BLK_BYTES);
-        const uint32_t sb = gg % 3;
-        if (tc::elect_one()) {
-          ab_mma_ss_128x64(tmem_base + sb * 64, q_addr, k_addr);                        // S  = Q K^T
-          ab_mma_ss_128x64(tmem_base + 192 + sb * 64, do_addr, k_addr + AB_BLK_BYTES);  // dP = dO V^T
-          tc::umma_commit(&s_full[sb]);
-        }
-        __syncwarp();
-      };
-      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
-        const int qt = w % p.n_tiles;
-        int dstart[2];
-        const int nb = ab_tile_block_plan(qt * 128, p.sep, p.T, nblk, dstart);
-        tc::mbar_wait(qdo_full, tcount & 1);
-        if (lane == 0) tr.log(10, tcount, 0);
-        // prologue: scores of the first two blocks
-        for (int pre = 0; pre < 2 && pre < nb; ++pre) {
-          const uint32_t gp = g + pre;
-          tc::mbar_wait(&kv_full[gp % AB_KS], (gp / AB_KS) & 1);
-          if (lane == 0) tr.log(11, tcount, pre);
-          tc::tc_fence_after();
-          issue_scores(gp);
-        }
-        // Barriers are probed one step early (see gemm_tc.cu: an MMA-warp stall is tensor-pipe idle time): the probe's
-        // round trip overlaps the blocking issue of the MMAs in between; the spinning wait is the fallback.
-        bool kv_ok = false;
-        for (int j = 0; j < nb; ++j, ++g) {
-          bool ds_ok = false;
-          if (j + 2 < nb) {
-            const uint32_t gn = g + 2;
-            if (!kv_ok) tc::mbar_wait(&kv_full[gn % AB_KS], (gn / AB_KS) & 1);
-            if (lane == 0) tr.log(11, tcount, j + 2);
-            tc::tc_fence_after();
-            ds_ok = tc::mbar_try_wait(&ds_ready[g % 3], (g / 3) & 1);
-            issue_scores(gn);       // its S/dP buffer was last read by dQ-MMA of block j-1, issued before (in-order pipe)
-          } else if (j + 2 == nb) {
-            if (tc::elect_one()) tc::umma_commit(qdo_empty);   // all score MMAs of this tile are issued
-            __syncwarp();
-          }
-          if (nb == 1 && j == 0) {
-            if (tc::elect_one()) tc::umma_commit(qdo_empty);
-            __syncwarp();
-          }
-          if (!ds_ok) tc::mbar_wait(&ds_ready[g % 3], (g / 3) & 1);
-          if (lane == 0) tr.log(12, tcount, j);
-          if (j == 0) tc::mbar_wait(dq_empty, (tcount & 1) ^ 1);
-          tc::tc_fence_after();
-          kv_ok = (j + 3 < nb) ? tc::mbar_try_wait(&kv_full[(g + 3) % AB_KS], ((g + 3) / AB_KS) & 1) : false;
-          const uint32_t k_addr = tc::smem_u32(sKV + (g % AB_KS) * 2 * AB_BLK_BYTES);
-          if (tc::elect_one()) {
-            ab_mma_ts_128x128(tmem_base + 384, tmem_base + (g % 3) * 64, k_addr, j > 0);     // dQ += dS K
-            tc::umma_commit(&kv_empty[g % AB_KS]);
-            if (j + 1 == nb) tc::umma_commit(dq_done);     // one phase per tile: the parity wait below is unambiguous
-          }
-          __syncwarp();
-          if (lane == 0) tr.log(13, tcount, j);
-        }
-      }
-    }
-  } else {
-    const int quarter = warp & 3;                 // TMEM lane quarter this warp may touch
-    const int half = (warp - 2) >> 2;             // which 32 of a block's 64 key columns this warp owns
-    const int row = quarter * 32 + lane;
-    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    tc::KernelTrace tr = tc::trace_make(p.trace, p.trace_cap, warp);   // one region per elementwise warp (2..9)
-    uint32_t g = 0, tcount = 0;
-    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
-      const int bh = w / p.n_tiles;
-      const int qt = w - bh * p.n_tiles;
-      const int b = bh / p.H, h = bh - b * p.H;
-      const int i0 = qt * 128;
-      const int i = i0 + row;
-      const bool valid = i < p.T;
-      const bool is_query = valid && i >= p.sep;
-      int dstart[2];
-      const int nb = ab_tile_block_plan(i0, p.sep, p.T, nblk, dstart);
-      tc::mbar_wait(qdo_full, tcount & 1);     // acquire the TMA-written Q / dO tiles (rows are read back in diagonal blocks)
-      float lse2 = INFINITY, dls = 0.f;       // dls = delta * scale
-      if (valid) {
-        lse2 = p.lse[static_cast<size_t>(bh) * p.T + i] * 1.4426950408889634f;
-        dls = p.delta[static_cast<size_t>(bh) * p.T + i] * p.scale;
-      }
-      for (int j = 0; j < nb; ++j, ++g) {
-        const uint32_t buf = g % 3;
-        tc::mbar_wait(&s_full[buf], (g / 3) & 1);
-        if (lane == 0) tr.log(20 + 100 * warp, tcount, j);
-        tc::tc_fence_after();
-        const bool dense = j < nblk;
-        const int kmax = dense ? p.sep - j * 64 : 0;
-        uint32_t s[32], dp[32], pk[16];
-        tc::tmem_ld_32x32b_x32(tmem_base + lane_off + buf * 64 + half * 32, s);
-        tc::tmem_ld_32x32b_x32(tmem_base + lane_off + 192 + buf * 64 + half * 32, dp);
-        tc::tmem_ld_wait();
-        if (dense && kmax >= 64) {
-#pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            const float p0 = tc::fast_exp2(fmaf(__uint_as_float(s[2 * c]), p.scale_log2, -lse2));
-            const float p1 = tc::fast_exp2(fmaf(__uint_as_float(s[2 * c + 1]), p.scale_log2, -lse2));
-            pk[c] = tc::pack_bf16x2(p0 * fmaf(__uint_as_float(dp[2 * c]), p.scale, -dls),
-                                    p1 * fmaf(__uint_as_float(dp[2 * c + 1]), p.scale, -dls));
-          }
-        } else if (dense) {
-#pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            const int k0 = half * 32 + 2 * c;
-            float d0 = 0.f, d1 = 0.f;
-            if (k0 < kmax)
-              d0 = tc::fast_exp2(fmaf(__uint_as_float(s[2 * c]), p.scale_log2, -lse2)) * fmaf(__uint_as_float(dp[2 * c]), p.scale, -dls);
-            if (k0 + 1 < kmax)
-              d1 = tc::fast_exp2(fmaf(__uint_as_float(s[2 * c + 1]), p.scale_log2, -lse2)) * fmaf(__uint_as_float(dp[2 * c + 1]), p.scale, -dls);
-            pk[c] = tc::pack_bf16x2(d0, d1);
-          }
-        } else {
-          int cl = -1;                                    // own column inside this warp's half, if any
-          {
-            const int c = i - dstart[j - nblk] - half * 32;
-            if (is_query && c >= 0 && c < 32) cl = c;
-          }
-          float sv = 0.f, dv = 0.f;
-#pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            sv = (c == cl) ? __uint_as_float(s[c]) : sv;
-            dv = (c == cl) ? __uint_as_float(dp[c]) : dv;
-          }
-          float dself = 0.f;
-          if (cl >= 0) {
-            // the diagonal key is attended by this row only: dK_i = dS_ii q_i and dV_i = P_ii dO_i are complete.
-            // Q / dO rows are read back from the (still live) swizzled smem tiles.
-            const float pii = tc::fast_exp2(fmaf(sv, p.scale_log2, -lse2));
-            dself = pii * fmaf(dv, p.scale, -dls);
-            const size_t tokq = p.batch_major ? static_cast<size_t>(b) * p.T + i : static_cast<size_t>(i) * p.B + b;
-            __nv_bfloat16* dkv_out = p.dqkv + tokq * p.ld_dqkv + h * AB_DH;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-              float qq[32], dd[32];
-              ab_load32_swz(sQ, row, c * 32, qq);
-              ab_load32_swz(sDO, row, c * 32, dd);
-#pragma unroll
-              for (int e = 0; e < 32; ++e) { qq[e] *= dself; dd[e] *= pii; }
-              ab_store32(dkv_out + E + c * 32, qq);
-              ab_store32(dkv_out + 2 * E + c * 32, dd);
-            }
-          }
-          const uint32_t lo = tc::pack_bf16x2(dself, 0.f), hi = tc::pack_bf16x2(0.f, dself);
-          const int cw = cl >> 1;                         // -1 >> 1 == -1: matches nothing
-          const uint32_t word = (cl & 1) ? hi : lo;
-#pragma unroll
-          for (int c = 0; c < 16; ++c) pk[c] = (c == cw) ? word : 0u;
-        }
-        tc::tmem_st_32x32b_x16(tmem_base + lane_off + buf * 64 + half * 16, pk);
-        tc::tmem_st_wait();
-        tc::tc_fence_before();
-        tc::mbar_arrive_warp(&ds_ready[buf]);
-        if (lane == 0) tr.log(21 + 100 * warp, tcount, j);
-      }
-      tc::mbar_arrive_warp(qdo_empty);                        // this thread no longer reads the Q / dO tiles
-      tc::mbar_wait(dq_done, tcount & 1);                     // committed once per tile, after its last dQ MMA
-      if (lane == 0) tr.log(22 + 100 * warp, tcount, 0);
-      tc::tc_fence_after();
-      const size_t tok = p.batch_major ? static_cast<size_t>(b) * p.T + (valid ? i : 0) : static_cast<size_t>(valid ? i : 0) * p.B + b;
-      __nv_bfloat16* dq_out = p.dqkv + tok * p.ld_dqkv + h * AB_DH;
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = half * 2 + cc;                      // the pair splits the four 32-column chunks
-        uint32_t raw[32];
-        float acc[32];
-        tc::tmem_ld_32x32b_x32(tmem_base + lane_off + 384 + c * 32, raw);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 32; ++e) acc[e] = __uint_as_float(raw[e]);
-        if (valid) ab_store32(dq_out + c * 32, acc);
-      }
-      tc::tc_fence_before();
-      tc::mbar_arrive_warp(dq_empty);
-      if (lane == 0) tr.log(23 + 100 * warp, tcount, 0);
-    }
-  }
-
-  tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc::tc_fence_after();
-    tc::tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -547,7 +260,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
           tc::tmem_ld_wait();
           tc::tc_fence_before();
           tc::mbar_arrive_warp(s_consumed);          // the score buffer may be overwritten by the next block's MMAs
-          if (key_ok) {
+          if (key_ok && p.drop_thr == 0) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
               const int col = half * 32 + 4 * c;
@@ -563,6 +276,26 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
                                            p1 * fmaf(__uint_as_float(dp[4 * c + 1]), p.scale, -dl.y));
               pkd[2 * c + 1] = tc::pack_bf16x2(p2 * fmaf(__uint_as_float(dp[4 * c + 2]), p.scale, -dl.z),
                                                p3 * fmaf(__uint_as_float(dp[4 * c + 3]), p.scale, -dl.w));
+            }
+          } else if (key_ok) {
+            // dropout on the probabilities (csrc/dropout.cuh): the keep bit of (query row i, key j) is byte j & 3 of the hash
+            // of (row id (b*H + h)*T + i, j >> 2); Pd = P m / (1 - p) feeds dV, dS = P (m dP / (1 - p) - delta) scale feeds dK
+            const float dsc = drop_scale(p.drop_thr);
+            const uint32_t rowbase = static_cast<uint32_t>(bh) * p.T + i * 64 + half * 32;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              float pv[2], dv[2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int cc = 2 * c + e;
+                const bool keep = drop_keep_byte(drop_hash(p.drop_seed, rowbase + cc, static_cast<uint32_t>(j) >> 2), j & 3, p.drop_thr);
+                const float mk = keep ? dsc : 0.f;
+                const float pr = tc::fast_exp2(fmaf(__uint_as_float(s[cc]), p.scale_log2, -stat[half * 32 + cc]));
+                pv[e] = pr * mk;
+                dv[e] = pr * fmaf(__uint_as_float(dp[cc]) * mk, p.scale, -stat[64 + half * 32 + cc]);
+              }
+              pkp[c] = tc::pack_bf16x2(pv[0], pv[1]);
+              pkd[c] = tc::pack_bf16x2(dv[0], dv[1]);
             }
           } else {
 #pragma unroll
@@ -623,7 +356,6 @@ using namespace pfn;
 extern "C" int pfn_attention_bwd_tc(const pfn_attn_desc* d, void* stream) {
   if (int rc = check_attn_desc_public(d, true, "attention_bwd_tc")) return rc;
   PFN_CHECK_ARG(d->dtype == PFN_BF16, "attention_bwd_tc: bf16 only");
-  PFN_CHECK_ARG(d->drop_thr == 0, "attention_bwd_tc: attention-probability dropout is implemented by the fp32-FMA kernels only");
   PFN_CHECK_ARG(d->dh == AB_DH, "attention_bwd_tc: head dim %d unsupported (built for 128)", d->dh);
   PFN_CHECK_ARG(d->ld_qkv % 8 == 0 && d->ld_out % 8 == 0 && d->ld_dout % 8 == 0 && d->ld_dqkv % 8 == 0,
                 "attention_bwd_tc: leading dims must be multiples of 8");
@@ -644,11 +376,11 @@ extern "C" int pfn_attention_bwd_tc(const pfn_attn_desc* d, void* stream) {
   p.dout = reinterpret_cast<const __nv_bfloat16*>(d->dout); p.ld_dout = d->ld_dout;
   p.dqkv = reinterpret_cast<__nv_bfloat16*>(d->dqkv); p.ld_dqkv = d->ld_dqkv;
   p.lse = d->lse; p.delta = d->delta; p.dq_colsum = d->dq_colsum;
+  p.drop_seed = d->drop_seed; p.drop_thr = d->drop_thr;
   p.batch_major = d->batch_major;
   p.trace = nullptr; p.trace_cap = g_trace_cap;
   static bool attr_set[64] = {};
   if (first_use_on_device(attr_set)) {
-    PFN_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
     PFN_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -662,19 +394,9 @@ extern "C" int pfn_attention_bwd_tc(const pfn_attn_desc* d, void* stream) {
     PFN_LAUNCH_OK();
   }
   if (only == 0 || only == 22) {
-    static const bool old_dq = []() { const char* e = getenv("PFN_ATTN_DQ_V1"); return e && e[0] == '1'; }();   // A/B only
-    if (!old_dq) {
-      p.trace = g_trace_which == 1 ? g_trace_ptr : nullptr;
-      if (int rc = launch_attn_bwd_dq(p, d, s)) return rc;
-      p.trace = nullptr;
-    } else {
-      p.n_tiles = (d->T + 127) / 128;
-      p.total_work = p.n_tiles * d->B * d->H;
-      int grid = num_sms() < p.total_work ? num_sms() : p.total_work;
-      p.trace = g_trace_which == 1 ? g_trace_ptr : nullptr;
-      attn_bwd_dq_v1_kernel<<<grid, AB_THREADS, AB_SMEM, s>>>(tmQKV128, tmQKV64, tmDO128, p);
-      p.trace = nullptr;
-    }
+    p.trace = g_trace_which == 1 ? g_trace_ptr : nullptr;
+    if (int rc = launch_attn_bwd_dq(p, d, s)) return rc;
+    p.trace = nullptr;
     PFN_LAUNCH_OK();
   }
   if (d->sep > 0 && (only == 0 || only == 21)) {

@@ -17,6 +17,7 @@
 //                             back to TMEM as packed bf16 over the S buffer; epilogue normalises O and stores.
 // TMEM map (256 columns): [0,64) S0 | [64,128) S1 | [128,256) O ; P_j aliases the first 32 columns of S_j.
 #include "common.cuh"
+#include "dropout.cuh"
 #include "tc_common.cuh"
 #include "../../include/pfn_b200.h"
 
@@ -45,6 +46,7 @@ struct AttnFwdParams {
   int batch_major;
   long long* trace;     // debug: clock64 event log of CTA 0 (null = off)
   int trace_cap;
+  uint32_t drop_seed; int drop_thr;   // dropout on the probabilities (thr 0 = off), csrc/dropout.cuh
 };
 
 // Block plan of one 128-row query tile: `nblk` dense blocks over the train keys [0, sep), followed by up to two
@@ -370,7 +372,20 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
           for (int c = 0; c < 32; ++c) pk[c] = (c == cw) ? word : 0u;
         }
-        l += psum;
+        l += psum;                      // the normaliser is over ALL visible keys; dropout only zeroes entries of P
+        if (p.drop_thr > 0) {
+          // packed word w of pk holds keys (2w, 2w + 1) of this block; four keys share one hash (csrc/dropout.cuh)
+          const uint32_t rid = static_cast<uint32_t>(bh) * p.T + i;
+          const uint32_t kb4 = static_cast<uint32_t>(dense ? j * ATT_BN : dstart[j - nblk]) >> 2;
+#pragma unroll
+          for (int q4 = 0; q4 < 16; ++q4) {
+            const uint32_t hsh = drop_hash(p.drop_seed, rid, kb4 + q4);
+            const uint32_t m0 = (drop_keep_byte(hsh, 0, p.drop_thr) ? 0x0000FFFFu : 0u) | (drop_keep_byte(hsh, 1, p.drop_thr) ? 0xFFFF0000u : 0u);
+            const uint32_t m1 = (drop_keep_byte(hsh, 2, p.drop_thr) ? 0x0000FFFFu : 0u) | (drop_keep_byte(hsh, 3, p.drop_thr) ? 0xFFFF0000u : 0u);
+            pk[2 * q4] &= m0;
+            pk[2 * q4 + 1] &= m1;
+          }
+        }
         tc::tmem_st_32x32b_x32(tmem_base + lane_off + buf * ATT_BN, pk);
         tc::tmem_st_wait();
         tc::tc_fence_before();
@@ -382,7 +397,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc::mbar_wait(o_done, tcount & 1);
       if (threadIdx.x == 64) tr.log(22, w, 0);     // epilogue start
       tc::tc_fence_after();
-      const float inv_l = 1.0f / l;
+      const float inv_l = (p.drop_thr > 0 ? drop_scale(p.drop_thr) : 1.0f) / l;     // kept probabilities are scaled by 1 / (1 - p)
       const size_t tokrow = p.batch_major ? static_cast<size_t>(b) * p.T + (valid ? i : 0) : static_cast<size_t>(valid ? i : 0) * p.B + b;
       __nv_bfloat16* orow = p.out + tokrow * p.ld_out + h * ATT_DH;
 #pragma unroll 1
@@ -441,7 +456,6 @@ using namespace pfn;
 extern "C" int pfn_attention_fwd_tc(const pfn_attn_desc* d, void* stream) {
   if (int rc = check_attn_desc_public(d, false, "attention_fwd_tc")) return rc;
   if (int rc = check_tc_attn(d, "attention_fwd_tc")) return rc;
-  PFN_CHECK_ARG(d->drop_thr == 0, "attention_fwd_tc: attention-probability dropout is implemented by the fp32-FMA kernels only");
   CUtensorMap tmQ, tmKV;
   const int E = d->H * d->dh;
   if (int rc = make_qkv_map(&tmQ, d->qkv, d->ld_qkv, 3 * E, d->B, d->T, ATT_BM, d->batch_major)) return rc;
@@ -457,6 +471,7 @@ extern "C" int pfn_attention_fwd_tc(const pfn_attn_desc* d, void* stream) {
   p.batch_major = d->batch_major;
   p.trace = g_trace_which == 0 ? g_trace_ptr : nullptr;
   p.trace_cap = g_trace_cap;
+  p.drop_seed = d->drop_seed; p.drop_thr = d->drop_thr;
   static bool attr_set[64] = {};
   if (first_use_on_device(attr_set)) {
     PFN_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWD_SMEM));

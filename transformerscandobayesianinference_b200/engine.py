@@ -102,8 +102,7 @@ class EncoderStackFn(torch.autograd.Function):
         ctx.needs_input_grad does not reflect no_grad); when False no activation is retained (inference memory).
         `drop`: None or (seed, thr) — training-mode dropout with probability thr/256 at the reference layer's four sites
         (attention probabilities, attention block output, after the GELU, MLP block output; torch
-        nn/modules/transformer.py:961-982).  Masks are counter-based and regenerated in backward (csrc/dropout.cuh); the
-        attention-probability site runs on the fp32-FMA attention kernels."""
+        nn/modules/transformer.py:961-982).  Masks are counter-based and regenerated in backward (csrc/dropout.cuh)."""
         L.require_cuda(src, *params)
         dt = act_dtype(precision)
         assert src.dtype == dt and src.dim() == 2
