@@ -21,6 +21,11 @@
 //   * Row statistics (lse, delta) of the next tile are requested a tile ahead.
 //   * dQ leaves through a swizzled smem staging tile and one TMA store instead of 16-byte stores to rows 1.5 MB apart.
 //
+// Tried and measured slower (round 2, same box): a 128-KEY-BLOCK variant (SS scores at N = 128, S double- / dP single-buffered
+// with early release, K/V ring of two 64 KB stages -- all that fits next to the Q / dO tile and the staging tile): 1.59 ms vs
+// 1.31 ms.  Half the MMA batches and polls per FLOP, but the next-but-one block's K/V can only be requested when this block's
+// dQ MMA has finished, and that 64 KB load is then exposed on every block (a third stage does not fit in 227 KB).
+//
 // TMEM map (512 columns):  S[2] @0,64 | dP[2] @128,192 | dQ @256..383 | Q (bf16 pairs) @384..447 | dO @448..511.
 // dS_j (packed bf16) aliases its own S buffer: keys 0..31 -> columns +0..15, keys 32..63 -> columns +32..47 (each half is
 // written by the warps that read exactly those score columns, so no thread overwrites scores another thread still needs).
