@@ -167,48 +167,62 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
     }
   } else if (warp == 1) {
     {
+      // MMA issuer.  Ring positions are (stage, phase) counters and every barrier is probed one batch early: a poll of an
+      // already-complete mbarrier costs the single issuing thread ~120 clocks of tensor-pipe idle time when the shallow
+      // tcgen05 queue has drained (tools/ubench/mma_gap.cu), so the probe's round trip is put under the blocking issue of
+      // the batch in between.
       const uint32_t k_addr = tc::smem_u32(sK), v_addr = tc::smem_u32(sV);
-      tc::KernelTrace tr = tc::trace_make(p.trace, p.trace_cap, 1);
+      const uint32_t qd_addr0 = tc::smem_u32(sQD);
+      int sst = 0;               // ring stage of the block whose SCORES are issued next
+      uint32_t sph = 0;
+      int ast = 0;               // ring stage of the block whose dV / dK MMAs are issued next
+      uint32_t nsc = 0;          // score batches issued so far
       uint32_t g = 0, tcount = 0;
-      auto issue_scores = [&](uint32_t gg) {
-        const uint32_t q_addr = tc::smem_u32(sQD + (gg % AB_KS) * 2 * AB_BLK_BYTES);
-        tc::mbar_wait(&qd_full[gg % AB_KS], (gg / AB_KS) & 1);
-        if (gg > 0) tc::mbar_wait(s_consumed, (gg - 1) & 1);      // the previous block's scores are in registers
+      bool qd_ok = false, sc_ok = false;     // early probe results for the NEXT score batch
+      auto issue_scores = [&]() {
+        const uint32_t q_addr = qd_addr0 + static_cast<uint32_t>(sst) * (2 * AB_BLK_BYTES);
+        if (!qd_ok) tc::mbar_wait(&qd_full[sst], sph);
+        if (nsc > 0 && !sc_ok) tc::mbar_wait(s_consumed, (nsc - 1) & 1);      // the previous block's scores are in registers
+        qd_ok = false; sc_ok = false;
         tc::tc_fence_after();
-        if (lane == 0) tr.log(11, tcount, gg);
         if (tc::elect_one()) {
           ab_mma_ss_128x64(tmem_base, k_addr, q_addr);                             // S^T  = K Q^T
           ab_mma_ss_128x64(tmem_base + 64, v_addr, q_addr + AB_BLK_BYTES);         // dP^T = V dO^T
           tc::umma_commit(st_full);
         }
         __syncwarp();
-        if (lane == 0) tr.log(14, tcount, gg);
+        ++nsc;
+        if (++sst == AB_KS) { sst = 0; sph ^= 1; }
       };
       for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
         tc::mbar_wait(kv_full, tcount & 1);
-        issue_scores(g);
+        issue_scores();
         for (int i = 0; i < nq; ++i, ++g) {
+          const uint32_t buf = g & 1;
+          bool pds_ok = false;
           if (i + 1 < nq) {
-            issue_scores(g + 1);
+            pds_ok = tc::mbar_try_wait(&pds_ready[buf], (g >> 1) & 1);     // early probe, consumed after the score batch
+            issue_scores();
           } else {
             if (tc::elect_one()) tc::umma_commit(kv_empty);
             __syncwarp();
           }
-          const uint32_t buf = g & 1;
-          tc::mbar_wait(&pds_ready[buf], (g >> 1) & 1);
-          if (lane == 0) tr.log(12, tcount, i);
+          if (!pds_ok) tc::mbar_wait(&pds_ready[buf], (g >> 1) & 1);
           if (i == 0) tc::mbar_wait(acc_empty, (tcount & 1) ^ 1);
           tc::tc_fence_after();
-          const uint32_t q_addr = tc::smem_u32(sQD + (g % AB_KS) * 2 * AB_BLK_BYTES);
+          // probes for the next score batch (this tile's block i+2, or the next tile's block 0: same ring, same counters)
+          qd_ok = tc::mbar_try_wait(&qd_full[sst], sph);
+          sc_ok = nsc > 0 && tc::mbar_try_wait(s_consumed, (nsc - 1) & 1);
+          const uint32_t q_addr = qd_addr0 + static_cast<uint32_t>(ast) * (2 * AB_BLK_BYTES);
           if (tc::elect_one()) {
             ab_mma_ts_128x128(tmem_base + 256, tmem_base + 128 + buf * 64, q_addr + AB_BLK_BYTES, i > 0);   // dV += P^T dO
             ab_mma_ts_128x128(tmem_base + 384, tmem_base + 160 + buf * 64, q_addr, i > 0);                  // dK += dS^T Q
-            tc::umma_commit(&qd_empty[g % AB_KS]);
+            tc::umma_commit(&qd_empty[ast]);
             tc::umma_commit(&pd_free[buf]);
             if (i + 1 == nq) tc::umma_commit(acc_done);    // one phase per tile
           }
           __syncwarp();
-          if (lane == 0) tr.log(13, tcount, i);
+          if (++ast == AB_KS) ast = 0;
         }
       }
     }
