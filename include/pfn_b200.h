@@ -27,7 +27,7 @@ extern "C" {
 #define PFN_B200_VERSION 1
 
 enum { PFN_F32 = 0, PFN_BF16 = 1 };
-enum { PFN_EPI_NONE = 0, PFN_EPI_GELU = 1, PFN_EPI_GELU_BWD = 2 };
+enum { PFN_EPI_NONE = 0, PFN_EPI_GELU = 1, PFN_EPI_GELU_BWD = 2, PFN_EPI_ROWDOT = 3 };
 enum { PFN_KERNEL_RBF = 0, PFN_KERNEL_MATERN12 = 1, PFN_KERNEL_MATERN32 = 2, PFN_KERNEL_MATERN52 = 3 };
 
 const char* pfn_last_error(void);
@@ -39,6 +39,9 @@ int pfn_num_sms(void);
  *   K-major operand : element (i,k) at base + i*ld + k;   MN-major operand : element (i,k) at base + k*ld + i
  *   epilogue GELU      : C = gelu_erf(acc+bias), optional C2 = acc+bias (pre-activation, saved for backward)
  *   epilogue GELU_BWD  : C = acc * gelu_erf'(aux)
+ *   epilogue ROWDOT    : C = acc (+bias), and rowdot_out[m * ceil(N / rowdot_width) + n / rowdot_width] += sum over the
+ *                        column group of C[m,n] * aux[m,n]   (fp32 atomics; aux is NOT added to C).  Used to produce
+ *                        delta = rowsum(dO * O) per (token, head) in the out-projection dgrad (tcgen05 path only).
  *   accumulate / k_splits>1 : atomic fp32 accumulation into C (weight gradients)
  * Replaces: nn.Linear / in_proj / out_proj / linear1 / linear2 / decoder GEMMs and their autograd backward
  *   (reference transformer.py:17-18,23,84-85; torch:nn/functional.py:6478; torch:nn/modules/transformer.py:980-982).
@@ -57,6 +60,8 @@ typedef struct pfn_gemm_desc {
   int accumulate;
   int k_splits;
   int ab_dtype;            /* dtype of A, B, aux, C2 (simt path; the tc path is bf16 only) */
+  float* rowdot_out;       /* epilogue ROWDOT: [M, ceil(N / rowdot_width)] fp32, accumulated (zero it first) */
+  int rowdot_width;        /* columns per group (the head dimension); must be a multiple of 128 */
 } pfn_gemm_desc;
 
 int pfn_gemm_bf16_tc(const pfn_gemm_desc* d, void* stream);
@@ -90,6 +95,10 @@ typedef struct pfn_attn_desc {
    * gradient), accumulated from the staged dQ tiles so that dqkv need not be re-read.  (The k third is zero in exact
    * arithmetic -- every row of dS sums to zero -- and the v third equals colsum(dO) = colsum(dz) W_out; see engine.py.) */
   float* dq_colsum;
+  /* backward, tcgen05 kernels only: 1 = `delta` already holds rowsum(dO * O) in TOKEN-major layout [T*B, H] (produced by the
+   * ROWDOT epilogue of the out-projection dgrad GEMM); the kernels then skip their own delta pass.  0 = `delta` is [B*H, T]
+   * scratch that the backward fills itself. */
+  int delta_token_major;
 } pfn_attn_desc;
 
 int pfn_attention_fwd_simt(const pfn_attn_desc* d, void* stream);

@@ -97,6 +97,26 @@ def test_gemm_tc_epilogues(cuda_device):
     assert (Cf - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("M,N,K,b_mn", [(640, 512, 512, True), (300, 256, 192, False), (4096, 512, 512, True)])
+def test_gemm_tc_rowdot(cuda_device, M, N, K, b_mn):
+    """ROWDOT epilogue: C is the plain product and rowdot[m, g] = sum over column group g of bf16(C[m, n]) * aux[m, n]
+    (the attention backward's delta = rowsum(dO * O) per head, produced by the out-projection dgrad)."""
+    torch.manual_seed(5)
+    width = 128
+    A = _operand(M, K, False, torch.bfloat16, cuda_device)
+    B = (_operand(N, K, b_mn, torch.bfloat16, cuda_device).float() * 0.05).to(torch.bfloat16)
+    aux = torch.randn(M, N, device=cuda_device).to(torch.bfloat16)
+    C = torch.empty(M, N, device=cuda_device, dtype=torch.bfloat16)
+    rd = torch.zeros(M, N // width, device=cuda_device, dtype=torch.float32)
+    L.gemm(A, B, C, b_mn_major=b_mn, aux=aux, epilogue=L.EPI_ROWDOT, rowdot=(rd, width), M=M, N=N, K=K, use_tc=True)
+    ref, _ = _ref(A, B, False, b_mn, None, None, L.EPI_NONE)
+    assert (C.float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()       # aux is NOT added to C
+    want = (C.float() * aux.float()).view(M, N // width, width).sum(-1)                  # exact w.r.t. the stored C
+    assert (rd - want).abs().max().item() <= 1e-4 * want.abs().max().item() + 1e-4
+    with pytest.raises(Exception):                                                       # group width must be a multiple of 128
+        L.gemm(A, B, C, b_mn_major=b_mn, aux=aux, epilogue=L.EPI_ROWDOT, rowdot=(rd, 64), M=M, N=N, K=K, use_tc=True)
+
+
 def test_gemm_tc_splitk_accumulate(cuda_device):
     torch.manual_seed(1)
     M, N, K = 512, 1536, 64 * 200  # wgrad shape: small output, long contraction

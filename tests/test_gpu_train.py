@@ -32,6 +32,30 @@ def test_fast_gp_get_batch_contract_and_covariance(cuda_device):
     assert torch.allclose(x3[:, 0, 0].cpu(), torch.linspace(0, 1, 8))
 
 
+@pytest.mark.parametrize("Bn", [128, 320])       # 128: one wave of 128-row tiles; 320 (> 2 x SM count): the 64-row-tile kernel
+def test_gp_sampler_factorises_the_cfg2_kernel_without_jitter(cuda_device, Bn):
+    """The BASELINE cfg-2 kernel matrix (1000 points, RBF lengthscale 0.6, noise 1e-4) has a condition number near 1e7: the
+    factorisation must go through in fp32 with NO failing pivot and no jitter (a 3xTF32 tensor-core variant of the update with
+    an explicit-inverse panel solve failed 2-4 % of such datasets and was backed out: profiles/r2_gp_sampler_ablation.md)."""
+    from transformerscandobayesianinference_b200 import _lib as L
+    T = 1000
+    ls = torch.full((Bn, 1), .6, device=cuda_device); os_ = torch.ones(Bn, device=cuda_device)
+    nz = torch.full((Bn,), 1e-4, device=cuda_device)
+    y = torch.empty(Bn, T, device=cuda_device); work = torch.empty(Bn, T, T, device=cuda_device)
+    for seed in range(3):
+        torch.manual_seed(seed)
+        x = torch.rand(Bn, T, 1, device=cuda_device); z = torch.randn(Bn, T, device=cuda_device)
+        info = torch.zeros(Bn, device=cuda_device, dtype=torch.int32)
+        L.gp_sample(x, z, ls, os_, nz, 0.0, 0, y, work, info)
+        assert int((info != 0).sum()) == 0, f"seed {seed}: failing pivots {info[info != 0][:8].tolist()}"
+        assert torch.isfinite(y).all()
+        if seed == 0:        # L L^T reproduces the kernel matrix (work holds the factor transposed: work[b][c][r] = L[r][c])
+            Lf = work[:4].transpose(1, 2).tril().double()
+            d = (x[:4, :, None, 0] - x[:4, None, :, 0]).double() / 0.6
+            K = torch.exp(-0.5 * d * d) + 1e-4 * torch.eye(T, device=cuda_device, dtype=torch.float64)
+            assert (Lf @ Lf.transpose(1, 2) - K).abs().max().item() < 2e-5
+
+
 def test_fast_gp_notebook_hyperparameters_are_factorisable(cuda_device):
     """noise 1e-4 / outputscale 1 / lengthscale .6 (SetupForGPFittingExperiments.ipynb) at T=1000: cond ~ 1e7."""
     torch.manual_seed(1)

@@ -22,7 +22,7 @@ L.load().pfn_debug_attention_trace(None, 0, 0)
 ev = [e for e in buf.view(NR * cap, 4).cpu().tolist() if e[3] != 0]
 ev.sort(key=lambda e: e[3])
 t0 = ev[0][3]
-names = {10: "M:QTready", 24: "T:copied", 1: "P:Qload", 2: "P:KVload", 11: "M:KVok+QK", 12: "M:Pready", 13: "M:PVissued", 20: "T:S", 21: "T:Ppub", 22: "T:epi0", 23: "T:epi1", 14: "M:QKissued", 24: "T:barsync"}
+names = {10: "M:QTready", 24: "T:copied", 1: "P:Qload", 2: "P:KVload", 3: "P:Vload", 11: "M:KVok+QK", 12: "M:Pready", 13: "M:PVissued", 20: "T:S", 21: "T:Ppub", 22: "T:epi0", 23: "T:epi1", 14: "M:QKissued", 24: "T:barsync"}
 # print the events of the first ~3 tiles after a warm start (skip first 2 tiles)
 for e in ev[:int(os.environ.get('TRACE_N', '1200'))]:
     code, wid = e[0] % 100, e[0] // 100

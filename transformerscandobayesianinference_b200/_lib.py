@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PFN_B200_LIB") or os.path.join(_HERE, "libpfn_b200.so")
 
 F32, BF16 = 0, 1
-EPI_NONE, EPI_GELU, EPI_GELU_BWD = 0, 1, 2
+EPI_NONE, EPI_GELU, EPI_GELU_BWD, EPI_ROWDOT = 0, 1, 2, 3
 KERNEL_RBF, KERNEL_MATERN12, KERNEL_MATERN32, KERNEL_MATERN52 = 0, 1, 2, 3
 
 c_int, c_float, c_void_p = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
@@ -29,6 +29,7 @@ class GemmDesc(ctypes.Structure):
         ("aux", c_void_p), ("ld_aux", c_int),
         ("C2", c_void_p), ("ldc2", c_int),
         ("epilogue", c_int), ("accumulate", c_int), ("k_splits", c_int), ("ab_dtype", c_int),
+        ("rowdot_out", c_void_p), ("rowdot_width", c_int),
     ]
 
 
@@ -43,7 +44,7 @@ class AttnDesc(ctypes.Structure):
         ("dqkv", c_void_p), ("ld_dqkv", c_int),
         ("delta", c_void_p), ("batch_major", c_int),
         ("drop_seed", ctypes.c_uint32), ("drop_thr", c_int),
-        ("dq_colsum", c_void_p),
+        ("dq_colsum", c_void_p), ("delta_token_major", c_int),
     ]
 
 
@@ -218,7 +219,7 @@ def _guarded(fn):
 # ------------------------------------------------------------------------------------------------
 @_guarded
 def gemm(A, B, C, *, a_mn_major=False, b_mn_major=False, bias=None, aux=None, C2=None, epilogue=EPI_NONE,
-         accumulate=False, k_splits=1, M=None, N=None, K=None, use_tc=None):
+         accumulate=False, k_splits=1, M=None, N=None, K=None, use_tc=None, rowdot=None):
     """C[M,N] (+)= epi(A . B^T-ish + bias) (+ aux).  Operands are 2-D row-major tensors (stride(1) == 1)."""
     lib = load()
     require_cuda(A, B, C, bias, aux, C2)
@@ -238,6 +239,9 @@ def gemm(A, B, C, *, a_mn_major=False, b_mn_major=False, bias=None, aux=None, C2
     d.C2, d.ldc2 = (C2.data_ptr(), C2.stride(0)) if C2 is not None else (None, 0)
     d.epilogue, d.accumulate, d.k_splits = epilogue, int(accumulate), k_splits
     d.ab_dtype = dtype_code(A)
+    if rowdot is not None:       # (fp32 [M, N // width] zeroed tensor, width): EPI_ROWDOT target
+        require_cuda(rowdot[0])
+        d.rowdot_out, d.rowdot_width = rowdot[0].data_ptr(), int(rowdot[1])
     if use_tc is None:
         use_tc = tc_gemm_ok(A, B, C, aux, C2)
     _count()
@@ -308,8 +312,9 @@ def attention_fwd(qkv, out, lse, T, B, H, dh, sep, use_tc=None, batch_major=Fals
 
 @_guarded
 def attention_bwd(qkv, out, lse, dout, dqkv, delta, T, B, H, dh, sep, use_tc=None, batch_major=False, drop=None,
-                  dq_colsum=None):
-    """dq_colsum (fp32 [H*dh], tcgen05 path only): += column sums of dQ, taken from the staged tiles inside the kernel."""
+                  dq_colsum=None, delta_token_major=False):
+    """dq_colsum (fp32 [H*dh], tcgen05 path only): += column sums of dQ, taken from the staged tiles inside the kernel.
+    delta_token_major: `delta` is a [T*B, H] tensor that already holds rowsum(dO * O) (GEMM ROWDOT epilogue)."""
     _count(2)
     lib = load()
     require_cuda(qkv, out, lse, dout, dqkv, delta, dq_colsum)
@@ -319,6 +324,9 @@ def attention_bwd(qkv, out, lse, dout, dqkv, delta, T, B, H, dh, sep, use_tc=Non
     if dq_colsum is not None:
         assert use_tc, "dq_colsum is produced by the tcgen05 backward only"
         d.dq_colsum = dq_colsum.data_ptr()
+    if delta_token_major:
+        assert use_tc, "a precomputed token-major delta is consumed by the tcgen05 backward only"
+        d.delta_token_major = 1
     fn = lib.pfn_attention_bwd_tc if use_tc else lib.pfn_attention_bwd_simt
     check(fn(ctypes.byref(d), stream_ptr()), "pfn_attention_bwd")
 

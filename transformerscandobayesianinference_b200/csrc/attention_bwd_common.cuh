@@ -24,6 +24,7 @@ struct AttnBwdParams {
   __nv_bfloat16* dqkv; int ld_dqkv;
   const float* lse;
   float* delta;
+  int delta_tm;          // 1: delta is token-major [T*B, H] and already filled (GEMM ROWDOT epilogue); 0: [B*H, T] scratch
   float* dq_colsum;      // optional [H*dh]: += column sums of dQ (dQ kernel epilogue)
   uint32_t drop_seed; int drop_thr;   // dropout on the attention probabilities (thr 0 = off), csrc/dropout.cuh
   int n_tiles;

@@ -294,7 +294,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
         if (i < p.T) {
           ok = true;
           lse_raw = __ldg(p.lse + static_cast<size_t>(bh) * p.T + i);
-          delta_raw = __ldg(p.delta + static_cast<size_t>(bh) * p.T + i);
+          delta_raw = p.delta_tm ? __ldg(p.delta + (static_cast<size_t>(i) * p.B + bh / p.H) * p.H + bh % p.H)
+                                 : __ldg(p.delta + static_cast<size_t>(bh) * p.T + i);
         }
       }
     };

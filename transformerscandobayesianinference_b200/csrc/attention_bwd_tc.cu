@@ -243,6 +243,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
       if (st_tid >= 128 || ww >= p.total_work) return 0.f;
       const int bh2 = ww / p.n_tiles;
       const int r = min(ii * 64 + (st_tid & 63), p.T - 1);
+      if (st_tid >= 64 && p.delta_tm) return __ldg(p.delta + (static_cast<size_t>(r) * p.B + bh2 / p.H) * p.H + bh2 % p.H);
       const float* src = st_tid < 64 ? p.lse : p.delta;
       return __ldg(src + static_cast<size_t>(bh2) * p.T + r);
     };
@@ -389,7 +390,8 @@ extern "C" int pfn_attention_bwd_tc(const pfn_attn_desc* d, void* stream) {
   p.out = reinterpret_cast<const __nv_bfloat16*>(d->out); p.ld_out = d->ld_out;
   p.dout = reinterpret_cast<const __nv_bfloat16*>(d->dout); p.ld_dout = d->ld_dout;
   p.dqkv = reinterpret_cast<__nv_bfloat16*>(d->dqkv); p.ld_dqkv = d->ld_dqkv;
-  p.lse = d->lse; p.delta = d->delta; p.dq_colsum = d->dq_colsum;
+  p.lse = d->lse; p.delta = d->delta; p.dq_colsum = d->dq_colsum; p.delta_tm = d->delta_token_major;
+  PFN_CHECK_ARG(!(d->delta_token_major && d->batch_major), "attention_bwd_tc: a token-major delta implies the reference token order");
   p.drop_seed = d->drop_seed; p.drop_thr = d->drop_thr;
   p.batch_major = d->batch_major;
   p.trace = nullptr; p.trace_cap = g_trace_cap;
@@ -400,7 +402,7 @@ extern "C" int pfn_attention_bwd_tc(const pfn_attn_desc* d, void* stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   // debug only (tools/time_kernels.py): pfn_debug_attention_trace(NULL, 0, 21|22|23) runs just dK/dV | dQ | delta
   const int only = (g_trace_ptr == nullptr && g_trace_which >= 21 && g_trace_which <= 23) ? g_trace_which : 0;
-  if (only == 0 || only == 23) {
+  if ((only == 0 || only == 23) && !d->delta_token_major) {
     const long long rows = static_cast<long long>(d->T) * d->B;
     long long grid = (rows + 7) / 8;
     if (grid > 8LL * num_sms()) grid = 8LL * num_sms();

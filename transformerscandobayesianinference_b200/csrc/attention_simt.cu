@@ -236,6 +236,7 @@ extern "C" int pfn_attention_fwd_simt(const pfn_attn_desc* d, void* stream) {
 extern "C" int pfn_attention_bwd_simt(const pfn_attn_desc* d, void* stream) {
   if (int rc = check_attn_desc(d, true, "attention_bwd_simt")) return rc;
   PFN_CHECK_ARG(d->batch_major == 0, "attention_bwd_simt: batch-major token order is only implemented by the tcgen05 kernels");
+  PFN_CHECK_ARG(d->delta_token_major == 0, "attention_bwd_simt: a precomputed token-major delta is only consumed by the tcgen05 kernels");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   return d->dtype == PFN_F32 ? dispatch_attn_simt<float>(d, true, s) : dispatch_attn_simt<__nv_bfloat16>(d, true, s);
 }

@@ -9,7 +9,12 @@
 // CPU time in exactly those copies).
 //
 // Forward, per CTA (two CTAs per SM so one CTA's softmax overlaps the other's MMAs):
-//   warp 0      TMA producer: Q tile (128 rows) once per work item, K/V blocks (64 keys) through a 2-stage ring
+//   warp 0      TMA producer: Q tile (128 rows) once per work item, K blocks (64 keys) through a 3-stage ring and V blocks
+//               through their own 2-stage ring.  K_j is needed a whole block before V_j (Q K_j^T is
+//               issued ahead of the softmax of block j-1, P_j V_j after the softmax of block j) and its stage is free as
+//               soon as Q K_j^T has completed, so separate rings let both loads run 2 blocks ahead inside the same 112 KB
+//               (a joint 2-stage K+V ring made every block wait ~1 300 clk for a load that could only be requested after
+//               P_{j-2} V_{j-2} had completed: profiles/r1_trace_attn_fwd_clock64.txt)
 //   warp 1      MMA issuer  : S_j = Q K_j^T  (SS, 128x64x128)  ->  TMEM S buffer (double buffered)
 //                             O  += P_j V_j  (TS, P read from TMEM, V MN-major from smem, 128x128x64)
 //   warps 2..5  softmax     : one thread per query row; tcgen05.ld S row, online softmax in the log2 domain with
@@ -28,11 +33,14 @@ int check_attn_desc_public(const pfn_attn_desc* d, bool bwd, const char* who);
 constexpr int ATT_BM = 128;
 constexpr int ATT_BN = 64;
 constexpr int ATT_DH = 128;
-constexpr int ATT_STAGES = 2;
+constexpr int ATT_NK = 3;                                  // K ring depth
+constexpr int ATT_NV = 2;                                  // V ring depth
 constexpr int ATT_THREADS = 192;
 constexpr int ATT_Q_BYTES = ATT_BM * ATT_DH * 2;          // 32 KB (two 64-wide chunks of 16 KB)
 constexpr int ATT_KV_BYTES = ATT_BN * ATT_DH * 2;         // 16 KB per operand (two chunks of 8 KB)
-constexpr int ATT_FWD_SMEM = ATT_Q_BYTES + ATT_STAGES * 2 * ATT_KV_BYTES + 256 + 1024;
+// No alignment slack: two CTAs of 112 KB + barriers must fit one SM, so the kernel relies on (and checks) a 1 KB-aligned
+// dynamic shared memory base instead of rounding the pointer up.
+constexpr int ATT_FWD_SMEM = ATT_Q_BYTES + (ATT_NK + ATT_NV) * ATT_KV_BYTES + 256;
 constexpr float kRescaleThreshold = 8.0f;                  // log2 units
 
 struct AttnFwdParams {
@@ -100,21 +108,26 @@ __device__ __forceinline__ float dot_rows128(const __nv_bfloat16* a, const __nv_
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                    const AttnFwdParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((tc::smem_u32(smem) & 1023u) != 0) __trap();        // the 128-byte-swizzled tiles need 1 KB alignment
   uint8_t* sQ = smem;
-  uint8_t* sKV = smem + ATT_Q_BYTES;   // stage s: K at sKV + s*32K, V at +16K
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_Q_BYTES + ATT_STAGES * 2 * ATT_KV_BYTES);
+  uint8_t* sK = smem + ATT_Q_BYTES;                          // stage s at + s * 16 KB
+  uint8_t* sV = sK + ATT_NK * ATT_KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATT_NV * ATT_KV_BYTES);
   uint64_t* q_full = bars + 0;
   uint64_t* q_empty = bars + 1;
-  uint64_t* kv_full = bars + 2;        // [2]
-  uint64_t* kv_empty = bars + 4;       // [2]
-  uint64_t* s_full = bars + 6;         // [2]
-  uint64_t* p_ready = bars + 8;        // [2]
-  uint64_t* pv_done = bars + 10;
-  uint64_t* o_empty = bars + 11;
-  uint64_t* o_done = bars + 12;        // one phase per tile: committed after the tile's last P V
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* k_full = bars + 2;                   // [ATT_NK]
+  uint64_t* k_empty = k_full + ATT_NK;           // [ATT_NK]
+  uint64_t* v_full = k_empty + ATT_NK;           // [ATT_NV]
+  uint64_t* v_empty = v_full + ATT_NV;           // [ATT_NV]
+  uint64_t* s_full = v_empty + ATT_NV;           // [2]
+  uint64_t* p_ready = s_full + 2;                // [2]
+  uint64_t* pv_done = p_ready + 2;
+  uint64_t* o_empty = pv_done + 1;
+  uint64_t* o_done = pv_done + 2;                // one phase per tile: committed after the tile's last P V
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 3);
+  static_assert((2 + 2 * ATT_NK + 2 * ATT_NV + 4 + 3) * 8 + 4 <= 256, "barrier block");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -127,9 +140,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (warp == 1 && lane == 0) {
     tc::mbar_init(q_full, 1);
     tc::mbar_init(q_empty, 1);
+    for (int s = 0; s < ATT_NK; ++s) { tc::mbar_init(&k_full[s], 1); tc::mbar_init(&k_empty[s], 1); }
+    for (int s = 0; s < ATT_NV; ++s) { tc::mbar_init(&v_full[s], 1); tc::mbar_init(&v_empty[s], 1); }
     for (int s = 0; s < 2; ++s) {
-      tc::mbar_init(&kv_full[s], 1);
-      tc::mbar_init(&kv_empty[s], 1);
       tc::mbar_init(&s_full[s], 1);
       tc::mbar_init(&p_ready[s], 4);      // one arrival per softmax warp
     }
@@ -150,41 +163,73 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   if (warp == 0) {
     // =============================================================== TMA producer (converged warp, elected lane issues)
+    // One warp feeds both rings.  The (tile, block) sequence is walked by two cursors, the K cursor two blocks ahead of the
+    // V cursor:  K0 K1 | V0 K2 | V1 K3 | ...   V_n waits for P_{n-2} V_{n-2} to complete, and by then Q K_{n-1}^T (which the
+    // MMA warp issues before P_{n-2} V_{n-2}) has freed the stage K_{n+2} goes to, so neither wait holds the other load back.
     {
       tc::KernelTrace tr = tc::trace_make(p.trace, p.trace_cap, 0);
-      uint32_t g = 0;      // running KV-block counter (ring position)
-      uint32_t tcount = 0; // running tile counter
-      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
-        const int bh = w / p.n_qtiles;
-        const int qt = w - bh * p.n_qtiles;
-        const int b = bh / p.H, h = bh - b * p.H;
-        const int i0 = qt * ATT_BM;
-        int dstart[2];
-        const int nb = tile_block_plan(i0, p.sep, p.T, nblk, dstart);
-        tc::mbar_wait(q_empty, (tcount & 1) ^ 1);
-        if (lane == 0) tr.log(1, tcount, 0);   // Q load issue
-        if (tc::elect_one()) {
-          tc::mbar_expect_tx(q_full, ATT_Q_BYTES);
-          tc::tma_load_3d(sQ, &tmQ, q_full, h * ATT_DH, b, i0);
-          tc::tma_load_3d(sQ + 16384, &tmQ, q_full, h * ATT_DH + 64, b, i0);
-        }
-        __syncwarp();
-        for (int j = 0; j < nb; ++j, ++g) {
-          const int st = g & 1;
-          tc::mbar_wait(&kv_empty[st], ((g >> 1) & 1) ^ 1);
-          if (lane == 0) tr.log(2, tcount, j);   // KV load issue
-          uint8_t* kdst = sKV + st * 2 * ATT_KV_BYTES;
-          uint8_t* vdst = kdst + ATT_KV_BYTES;
-          const int j0 = j < nblk ? j * ATT_BN : dstart[j - nblk];
+      struct Cursor { int w, j, nb, b, h, i0; int dstart[2]; uint32_t tcount; bool valid; };
+      auto enter = [&](Cursor& c) {
+        c.valid = c.w < p.total_work;
+        if (!c.valid) return;
+        const int bh = c.w / p.n_qtiles;
+        const int qt = c.w - bh * p.n_qtiles;
+        c.b = bh / p.H; c.h = bh - c.b * p.H;
+        c.i0 = qt * ATT_BM;
+        c.nb = tile_block_plan(c.i0, p.sep, p.T, nblk, c.dstart);
+        c.j = 0;
+      };
+      auto advance = [&](Cursor& c) {
+        if (++c.j == c.nb) { c.w += gridDim.x; ++c.tcount; enter(c); }
+      };
+      int kst = 0, vst = 0; uint32_t kph = 0, vph = 0;
+      auto issue_k = [&](Cursor& c) {
+        if (!c.valid) return;
+        if (c.j == 0) {
+          tc::mbar_wait(q_empty, (c.tcount & 1) ^ 1);
+          if (lane == 0) tr.log(1, c.tcount, 0);   // Q load issue
           if (tc::elect_one()) {
-            tc::mbar_expect_tx(&kv_full[st], 2 * ATT_KV_BYTES);
-            tc::tma_load_3d(kdst, &tmKV, &kv_full[st], E + h * ATT_DH, b, j0);
-            tc::tma_load_3d(kdst + 8192, &tmKV, &kv_full[st], E + h * ATT_DH + 64, b, j0);
-            tc::tma_load_3d(vdst, &tmKV, &kv_full[st], 2 * E + h * ATT_DH, b, j0);
-            tc::tma_load_3d(vdst + 8192, &tmKV, &kv_full[st], 2 * E + h * ATT_DH + 64, b, j0);
+            tc::mbar_expect_tx(q_full, ATT_Q_BYTES);
+            tc::tma_load_3d(sQ, &tmQ, q_full, c.h * ATT_DH, c.b, c.i0);
+            tc::tma_load_3d(sQ + 16384, &tmQ, q_full, c.h * ATT_DH + 64, c.b, c.i0);
           }
           __syncwarp();
         }
+        tc::mbar_wait(&k_empty[kst], kph ^ 1);
+        if (lane == 0) tr.log(2, c.tcount, c.j);   // K load issue
+        uint8_t* kdst = sK + kst * ATT_KV_BYTES;
+        const int j0 = c.j < nblk ? c.j * ATT_BN : c.dstart[c.j - nblk];
+        if (tc::elect_one()) {
+          tc::mbar_expect_tx(&k_full[kst], ATT_KV_BYTES);
+          tc::tma_load_3d(kdst, &tmKV, &k_full[kst], E + c.h * ATT_DH, c.b, j0);
+          tc::tma_load_3d(kdst + 8192, &tmKV, &k_full[kst], E + c.h * ATT_DH + 64, c.b, j0);
+        }
+        __syncwarp();
+        if (++kst == ATT_NK) { kst = 0; kph ^= 1; }
+        advance(c);
+      };
+      auto issue_v = [&](Cursor& c) {
+        tc::mbar_wait(&v_empty[vst], vph ^ 1);
+        if (lane == 0) tr.log(3, c.tcount, c.j);   // V load issue
+        uint8_t* vdst = sV + vst * ATT_KV_BYTES;
+        const int j0 = c.j < nblk ? c.j * ATT_BN : c.dstart[c.j - nblk];
+        if (tc::elect_one()) {
+          tc::mbar_expect_tx(&v_full[vst], ATT_KV_BYTES);
+          tc::tma_load_3d(vdst, &tmKV, &v_full[vst], 2 * E + c.h * ATT_DH, c.b, j0);
+          tc::tma_load_3d(vdst + 8192, &tmKV, &v_full[vst], 2 * E + c.h * ATT_DH + 64, c.b, j0);
+        }
+        __syncwarp();
+        if (++vst == ATT_NV) { vst = 0; vph ^= 1; }
+        advance(c);
+      };
+      Cursor ck, cv;
+      ck.w = cv.w = blockIdx.x; ck.tcount = cv.tcount = 0;
+      enter(ck); enter(cv);
+      issue_k(ck);
+      issue_k(ck);
+      while (cv.valid) {
+        issue_v(cv);
+        issue_k(ck);
       }
     }
   } else if (warp == 1) {
@@ -197,9 +242,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const uint32_t q_addr = tc::smem_u32(sQ);
       tc::KernelTrace tr = tc::trace_make(p.trace, p.trace_cap, 1);
       uint32_t g = 0, tcount = 0;
+      int kst = 0; uint32_t kph = 0;     // K ring position of the NEXT Q K^T batch
+      int vst = 0; uint32_t vph = 0;     // V ring position of the NEXT P V batch
       auto issue_qk = [&](uint32_t gg) {
-        const int st = gg & 1;
-        const uint32_t k_addr = tc::smem_u32(sKV + st * 2 * ATT_KV_BYTES);
+        tc::mbar_wait(&k_full[kst], kph);
+        if (lane == 0) tr.log(11, tcount, static_cast<int>(gg));   // K landed
+        tc::tc_fence_after();
+        const uint32_t k_addr = tc::smem_u32(sK + kst * ATT_KV_BYTES);
         const uint32_t d_tmem = tmem_base + (gg & 1) * ATT_BN;
         if (tc::elect_one()) {
 #pragma unroll
@@ -209,8 +258,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             tc::umma_bf16_ss(d_tmem, a_desc, b_desc, idesc_qk, kk > 0 ? 1u : 0u);
           }
           tc::umma_commit(&s_full[gg & 1]);
+          tc::umma_commit(&k_empty[kst]);        // the K stage is free as soon as this batch has completed
         }
         __syncwarp();
+        if (++kst == ATT_NK) { kst = 0; kph ^= 1; }
       };
       for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
         const int qt = w % p.n_qtiles;
@@ -218,29 +269,23 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int nb = tile_block_plan(qt * ATT_BM, p.sep, p.T, nblk, dstart);
         tc::mbar_wait(q_full, tcount & 1);
         if (lane == 0) tr.log(10, tcount, 0);  // Q landed
-        tc::mbar_wait(&kv_full[g & 1], (g >> 1) & 1);
-        if (lane == 0) tr.log(11, tcount, 0);  // KV0 landed
-        tc::tc_fence_after();
         issue_qk(g);
         for (int j = 0; j < nb; ++j, ++g) {
           bool p_ok = false;        // p_ready probed before the (blocking) Q K^T issue; see gemm_tc.cu on early probes
           if (j + 1 < nb) {
-            const uint32_t gn = g + 1;
-            tc::mbar_wait(&kv_full[gn & 1], (gn >> 1) & 1);
-            if (lane == 0) tr.log(11, tcount, j + 1);
-            tc::tc_fence_after();
             p_ok = tc::mbar_try_wait(&p_ready[g & 1], (g >> 1) & 1);
-            issue_qk(gn);
+            issue_qk(g + 1);
           } else {
             if (tc::elect_one()) tc::umma_commit(q_empty);   // every QK^T of this tile has been issued
             __syncwarp();
           }
+          const bool v_ok = tc::mbar_try_wait(&v_full[vst], vph);
           if (!p_ok) tc::mbar_wait(&p_ready[g & 1], (g >> 1) & 1);
           if (lane == 0) tr.log(12, tcount, j);  // P ready seen by MMA warp
           if (j == 0) tc::mbar_wait(o_empty, (tcount & 1) ^ 1);
+          if (!v_ok) tc::mbar_wait(&v_full[vst], vph);
           tc::tc_fence_after();
-          const int st = g & 1;
-          const uint32_t v_addr = tc::smem_u32(sKV + st * 2 * ATT_KV_BYTES + ATT_KV_BYTES);
+          const uint32_t v_addr = tc::smem_u32(sV + vst * ATT_KV_BYTES);
           const uint32_t p_tmem = tmem_base + (g & 1) * ATT_BN;
           const uint32_t o_tmem = tmem_base + 128;
           if (tc::elect_one()) {
@@ -249,11 +294,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               const uint64_t b_desc = tc::umma_smem_desc(v_addr + kk * 2048, 8192, 1024);
               tc::umma_bf16_ts(o_tmem, p_tmem + kk * 8, b_desc, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
             }
-            tc::umma_commit(&kv_empty[st]);
+            tc::umma_commit(&v_empty[vst]);
             tc::umma_commit(pv_done);
             if (j + 1 == nb) tc::umma_commit(o_done);
           }
           __syncwarp();
+          if (++vst == ATT_NV) { vst = 0; vph ^= 1; }
           if (lane == 0) tr.log(13, tcount, j);  // PV issued
         }
       }

@@ -48,6 +48,8 @@ struct GemmTcParams {
   int l2_prefetch;               // 1 => the producer prefetches the next work item's A tile into L2
   long long* stall;              // debug: per-CTA [8] clock sums: producer wait-empty, MMA wait-full, MMA wait-tempty, epilogue wait-tfull, epilogue wait-staging (store read + group barrier), epilogue column loop, of which tcgen05.wait::ld
   int tma_store;                 // 1 => bf16 C (and C2) leave through the smem staging buffer + TMA store
+  float* rowdot_out;             // PFN_EPI_ROWDOT: [M, rowdot_groups] fp32, += sum over a column group of C * aux
+  int rowdot_width, rowdot_groups;
 };
 
 constexpr int kBlockM = 128;
@@ -332,6 +334,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool row_ok = row < p.M;
       const bool add_bias = p.bias != nullptr && split == 0;
       const bool aux_now = use_aux && row_ok && (p.act == PFN_EPI_GELU_BWD || split == 0);
+      float rowdot = 0.f;          // PFN_EPI_ROWDOT: this thread's share of sum_n C[row, n] * aux[row, n]
       const int gcol0 = n0 + half * COLS_PER_GROUP + sub * kCW;          // first column this THREAD handles (step 0)
       // Software pipeline: the aux (residual / pre-activation) row segment and the TMEM piece of step c+1 are requested
       // before step c is computed; the very first aux request goes out before the accumulator is even complete.
@@ -476,6 +479,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int i = 0; i < kCW; ++i) f[i] *= gelu_grad_fast(a[i]);
 #endif
+            } else if (p.act == PFN_EPI_ROWDOT) {
+              // the products use the bf16-ROUNDED outputs (what the consumer of C will read), so that the row sum is
+              // exactly the dot product of the stored C with aux
+#pragma unroll
+              for (int i = 0; i < kCW; ++i) rowdot = fmaf(__bfloat162float(__float2bfloat16_rn(f[i])), a[i], rowdot);
             } else {
 #pragma unroll
               for (int i = 0; i < kCW; ++i) f[i] += a[i];
@@ -526,6 +534,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         if (p.stall != nullptr) st_cols += clock64() - tc0;
+        if (p.act == PFN_EPI_ROWDOT && row_ok && gcol0 < p.N)      // all columns this thread swept lie in ONE group (width % 128 == 0)
+          atomicAdd(p.rowdot_out + static_cast<size_t>(row) * p.rowdot_groups + gcol0 / p.rowdot_width, rowdot);
         if (pass == npass - 1) {
           // accumulator stage drained: hand it back to the MMA warp
           tc::tc_fence_before();
@@ -617,6 +627,8 @@ static int launch_gemm_tc(const pfn_gemm_desc* d, cudaStream_t stream) {
   p.C = d->C; p.ldc = d->ldc; p.c_f32 = d->c_dtype == PFN_F32;
   p.C2 = reinterpret_cast<__nv_bfloat16*>(d->C2); p.ldc2 = d->ldc2;
   p.act = d->epilogue;
+  p.rowdot_out = d->rowdot_out; p.rowdot_width = d->rowdot_width > 0 ? d->rowdot_width : 1;
+  p.rowdot_groups = (d->N + p.rowdot_width - 1) / p.rowdot_width;
   constexpr int kTileM = CTA2 ? 2 * kBlockM : kBlockM;
   p.tiles_m = (d->M + kTileM - 1) / kTileM;
   p.tiles_n = (d->N + BLOCK_N - 1) / BLOCK_N;
@@ -666,7 +678,10 @@ extern "C" int pfn_gemm_bf16_tc(const pfn_gemm_desc* d, void* stream) {
   PFN_CHECK_ARG(d->M > 0 && d->N > 0 && d->K > 0, "gemm_tc: empty problem %d x %d x %d", d->M, d->N, d->K);
   PFN_CHECK_ARG(d->lda % 8 == 0 && d->ldb % 8 == 0, "gemm_tc: lda/ldb must be multiples of 8 elements (got %d, %d)",
                 d->lda, d->ldb);
-  PFN_CHECK_ARG(d->epilogue >= 0 && d->epilogue <= PFN_EPI_GELU_BWD, "gemm_tc: bad epilogue %d", d->epilogue);
+  PFN_CHECK_ARG(d->epilogue >= 0 && d->epilogue <= PFN_EPI_ROWDOT, "gemm_tc: bad epilogue %d", d->epilogue);
+  PFN_CHECK_ARG(d->epilogue != PFN_EPI_ROWDOT || (d->aux != nullptr && d->rowdot_out != nullptr && d->rowdot_width >= 128 &&
+                                                  d->rowdot_width % 128 == 0 && d->k_splits <= 1 && !d->accumulate),
+                "gemm_tc: ROWDOT epilogue needs aux, rowdot_out, a group width that is a multiple of 128 and no split-K");
   PFN_CHECK_ARG(d->epilogue != PFN_EPI_GELU_BWD || d->aux != nullptr, "gemm_tc: GELU' epilogue needs aux = pre-activation");
   const bool vec_ok = (d->c_dtype == PFN_F32 ? d->ldc % 4 == 0 : d->ldc % 8 == 0) &&
                       (reinterpret_cast<uintptr_t>(d->C) & 15) == 0;

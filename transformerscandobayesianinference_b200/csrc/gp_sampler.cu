@@ -6,21 +6,10 @@
 // and, with per-dataset hyperparameters and Matern-nu kernels, priors/fast_gp_mix.py:24-55,88-99.
 //
 // Left-looking, panel width 32:  for panel p (columns c0..c0+31)
-//     U[r, :]  = K[r, c0:c0+32] - L[r, 0:c0] L[c0:c0+32, 0:c0]^T          (128x32 tiles; the T^3/3 flops of the factorisation)
-//     L11      = chol(U[c0:c0+32, :]),  W = L11^-1                        (one warp, rows / columns in registers, shuffles)
-//     L[r, c0:c0+32] = U[r, :] W^T  for r > c0+31                         (a 128x32x32 product for all eight warps)
+//     U[r, :]  = K[r, c0:c0+32] - L[r, 0:c0] L[c0:c0+32, 0:c0]^T          (128x32 tiles, 4x4 register micro-tiles)
+//     L11      = chol(U[c0:c0+32, :])                                     (one warp, rows in registers, shuffles)
+//     L[r, c0:c0+32] = U[r, :] L11^-T  for r > c0+31                      (one thread per row, L11 broadcast from smem)
 //     y[r]    += L[r, c0:c0+32] . z[c0:c0+32]
-// Both products run on the tensor cores as 3xTF32 (`mma.sync.m16n8k8.tf32`): every fp32 operand is split into hi = tf32(a)
-// and lo = tf32(a - hi) and the product is accumulated as lo*hi + hi*lo + hi*hi in fp32, which keeps ~21 bits of each
-// operand -- the factor passes the same fp32 residual tests (||L L^T - K|| <= 2e-5 ||K||) as the FFMA version of round 1.
-// Why (ncu --set full of the round-1 kernel, profiles/r2_ncu_gp_sample.md): 33 % of the warp samples sat at the barrier
-// behind the panel solve -- one thread per row running 496 DEPENDENT FMAs while half the CTA idled -- and 45 % in the FFMA
-// update loop at 54 % issue utilisation.  Multiplying by the explicit inverse of the 32x32 diagonal block (formed once per
-// panel by the warp that factors it) turns the solve into the same fully parallel product as the update.
-// Where the time goes now (ablation builds, 296 datasets of T = 1000 on one B200, profiles/r2_gp_sampler_ablation.md):
-// 4.79 ms total = update products 1.9 (the legacy mma.sync path delivers 506 tf32 MAC/clk/SM, 1/8 of tcgen05 -- with the
-// three-way split only 1.3x the FFMA rate, tools/ubench/mma_sync_rate.cu) + panel streaming 1.0 + diagonal block 0.9 +
-// solve 0.44 + factor stores 0.26 + rest 0.3.  The next step is the update on tcgen05 kind::tf32 with hi/lo smem tiles.
 // K is never materialised; the only HBM traffic is writing the factor once and re-reading finished panels.
 // The factor is kept TRANSPOSED in `work` (work[b][c][r] = L[r][c]): panel re-reads become contiguous rows that stream
 // through a 3-stage cp.async ring straight into the k-major smem tiles, and the panel write-back is coalesced.
@@ -30,12 +19,8 @@
 namespace pfn {
 
 constexpr int NB = 32;        // panel width
-constexpr int TR = 128;       // rows per update tile
 constexpr int GP_MAX_F = 128;
 constexpr int GP_STAGES = 3;
-constexpr int LDR = TR + 8;   // smem row strides (floats) of the k-major ring tiles and of the U tile: +8 / +4 keep the
-constexpr int LDC = NB + 8;   // mma.sync fragment loads (4 k-rows x 8 consecutive elements per instruction) conflict-free
-constexpr int LDU = NB + 4;
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
   const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
@@ -57,52 +42,22 @@ __device__ __forceinline__ float gp_kernel_value(float d2, float os, int kernel_
   return os * (1.0f + a + (5.0f / 3.0f) * d2) * expf(-a);
 }
 
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  const float rest = x - __uint_as_float(hi);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(rest));
-}
-// D (16x8, fp32) += A (16x8, tf32, row) * B (8x8, tf32, col)
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
-// acc[nt] (16 x 8 tiles nt = 0..3 of a 16 x 32 result) += A[16 x 8*KSTEPS] B[8*KSTEPS x 32] as 3xTF32.
-//   A(row, k) = Abase[k * lda_k + row * lda_r]   rows = this warp's 16 rows;   B(k, n) = Bbase[k * ldb_k + n * ldb_n]
-template <int KSTEPS>
-__device__ __forceinline__ void mma_3xtf32_16x32(float (&acc)[4][4], const float* Abase, int lda_k, int lda_r, const float* Bbase,
-                                                 int ldb_k, int ldb_n, int fg, int ft) {
-#pragma unroll
-  for (int ks = 0; ks < KSTEPS; ++ks) {
-    const int k0 = ks * 8;
-    uint32_t ah[4], al[4];
-    split_tf32(Abase[(k0 + ft) * lda_k + fg * lda_r], ah[0], al[0]);
-    split_tf32(Abase[(k0 + ft) * lda_k + (fg + 8) * lda_r], ah[1], al[1]);
-    split_tf32(Abase[(k0 + ft + 4) * lda_k + fg * lda_r], ah[2], al[2]);
-    split_tf32(Abase[(k0 + ft + 4) * lda_k + (fg + 8) * lda_r], ah[3], al[3]);
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      uint32_t bh[2], bl[2];
-      split_tf32(Bbase[(k0 + ft) * ldb_k + (nt * 8 + fg) * ldb_n], bh[0], bl[0]);
-      split_tf32(Bbase[(k0 + ft + 4) * ldb_k + (nt * 8 + fg) * ldb_n], bh[1], bl[1]);
-      mma_tf32(acc[nt], al, bh);       // small terms first
-      mma_tf32(acc[nt], ah, bl);
-      mma_tf32(acc[nt], ah, bh);
-    }
-  }
-}
-
-__global__ void __launch_bounds__(256, 2)
+// TR = rows per update tile; the CTA has 2 TR threads.  TR = 64 (128 threads, 49 KB of shared memory, 4 CTAs per SM) keeps four
+// independent datasets on an SM, so that the serial phases of one (32x32 diagonal block in one warp, row solves, ring
+// fill) overlap the products of the others, and 512 datasets fit in ONE wave of 592 slots (TR = 128: 2 CTAs per SM, 296
+// slots, two waves).
+template <int TR>
+__global__ void __launch_bounds__(2 * TR, TR == 64 ? 4 : 2)
 gp_sample_kernel(const float* __restrict__ x, const float* __restrict__ z, const float* __restrict__ ls,
                  const float* __restrict__ os_arr, const float* __restrict__ noise_arr, float jitter, int kernel_type,
                  float* __restrict__ y, float* work, int* __restrict__ info, int T, int F, int ldw) {
-  extern __shared__ __align__(16) float gp_dyn[];         // the cp.async ring lives in dynamic shared memory
-  float (*sR)[NB][LDR] = reinterpret_cast<float (*)[NB][LDR]>(gp_dyn);                            // sR[s][k][r] = L[r0 + r, j0 + k]
-  float (*sC)[NB][LDC] = reinterpret_cast<float (*)[NB][LDC]>(gp_dyn + GP_STAGES * NB * LDR);     // sC[s][k][c] = L[c0 + c, j0 + k]
-  __shared__ float sU[TR][LDU];                     // updated tile, then the solved panel rows (row-major, padded)
+  extern __shared__ __align__(16) float gp_dyn[];         // the cp.async ring lives in dynamic shared memory (60 KB)
+  constexpr int NT = 2 * TR;                                                                      // threads per CTA
+  float (*sR)[NB][TR] = reinterpret_cast<float (*)[NB][TR]>(gp_dyn);                              // sR[s][k][r] = L[r0 + r, j0 + k]
+  float (*sC)[NB][NB] = reinterpret_cast<float (*)[NB][NB]>(gp_dyn + GP_STAGES * NB * TR);        // sC[s][k][c] = L[c0 + c, j0 + k]
+  __shared__ float sU[TR][NB + 1];                  // updated tile, row-major (padded)
   __shared__ __align__(16) float sL[NB][NB];        // L11 (row-major), unit rows past the matrix edge
-  __shared__ float sW[NB][LDU];                     // W = L11^-1 (row-major, lower triangular)
+  __shared__ float sLinv[NB];
   __shared__ float sz[NB];
   __shared__ float s_inv_ls[GP_MAX_F];
   __shared__ int s_info;
@@ -110,9 +65,6 @@ gp_sample_kernel(const float* __restrict__ x, const float* __restrict__ z, const
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
   const int lane = tid & 31;
-  const int wrp = tid >> 5;  // warp w owns rows 16 w .. 16 w + 15 of a 128-row tile, all 32 panel columns
-  const int fg = lane >> 2;  // mma.sync fragment coordinates: row within 8 / column ...
-  const int ft = lane & 3;   // ... and k index / column pair
   const float* xb = x + static_cast<size_t>(b) * T * F;
   const float* zb = z + static_cast<size_t>(b) * T;
   float* yb = y + static_cast<size_t>(b) * T;
@@ -120,17 +72,19 @@ gp_sample_kernel(const float* __restrict__ x, const float* __restrict__ z, const
   const float os = os_arr[b];
   const float diag_add = noise_arr[b] + jitter;
 
-  for (int f = tid; f < F; f += blockDim.x) s_inv_ls[f] = 1.0f / ls[static_cast<size_t>(b) * F + f];
+  for (int f = tid; f < F; f += NT) s_inv_ls[f] = 1.0f / ls[static_cast<size_t>(b) * F + f];
   if (tid == 0) s_info = 0;
-  for (int r = tid; r < T; r += blockDim.x) yb[r] = 0.f;
+  for (int r = tid; r < T; r += NT) yb[r] = 0.f;
   __syncthreads();
+
+  const int ty = tid >> 3;   // 0..TR/4-1 -> rows ty*4 .. ty*4+3 of the tile
+  const int tx = tid & 7;    // 0..7  -> cols tx*4 .. tx*4+3 of the panel
 
   for (int c0 = 0; c0 < T; c0 += NB) {
     const int nb = min(NB, T - c0);
     if (tid < NB) sz[tid] = (c0 + tid < T) ? zb[c0 + tid] : 0.f;
     for (int r0 = c0; r0 < T; r0 += TR) {
       // ---------------------------------------------------------------- update: acc = L[r,0:c0] L[c,0:c0]^T
-      // acc[nt][j]: C fragment of the 16 x 8 tile nt -> (row 16 w + fg + 8 (j >> 1), column 8 nt + 2 ft + (j & 1))
       float acc[4][4];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
@@ -141,16 +95,17 @@ gp_sample_kernel(const float* __restrict__ x, const float* __restrict__ z, const
       auto issue = [&](int ch) {
         const int st = ch % GP_STAGES;
         const int j0 = ch * NB;
-        // sR: 32 k-rows x 128 floats = 1024 16-byte pieces; sC: 32 x 32 floats = 256 pieces; 5 per thread
+        // sR: 32 k-rows x TR floats = 8 TR 16-byte pieces (4 per thread); sC: 32 x 32 floats = 256 pieces
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int piece = tid + q * 256;
-          const int k = piece >> 5, r4 = (piece & 31) * 4;
+          const int piece = tid + q * NT;
+          const int k = piece / (TR / 4), r4 = (piece % (TR / 4)) * 4;
           const int r = r0 + r4;
           cp_async16(&sR[st][k][r4], Lt + static_cast<size_t>(j0 + k) * ldw + r, r < ldw);
         }
-        {
-          const int k = tid >> 3, c4 = (tid & 7) * 4;
+#pragma unroll
+        for (int piece = tid; piece < 256; piece += NT) {
+          const int k = piece >> 3, c4 = (piece & 7) * 4;
           const int c = c0 + c4;
           cp_async16(&sC[st][k][c4], Lt + static_cast<size_t>(j0 + k) * ldw + c, c < ldw);
         }
@@ -166,8 +121,17 @@ gp_sample_kernel(const float* __restrict__ x, const float* __restrict__ z, const
         if (ch + GP_STAGES - 1 < nch) issue(ch + GP_STAGES - 1);
         cp_async_commit();
         const int st = ch % GP_STAGES;
-        // A(row, k) = sR[st][k][16 w + row],  B(k, n) = sC[st][k][n]
-        mma_3xtf32_16x32<NB / 8>(acc, &sR[st][0][wrp * 16], LDR, 1, &sC[st][0][0], LDC, 1, fg, ft);
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+          const float4 a = *reinterpret_cast<const float4*>(&sR[st][k][ty * 4]);
+          const float4 bb = *reinterpret_cast<const float4*>(&sC[st][k][tx * 4]);
+          const float av[4] = {a.x, a.y, a.z, a.w};
+          const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
       }
       cp_async_wait<0>();
       __syncthreads();     // every thread is done with the ring before the next tile refills it
@@ -180,42 +144,37 @@ gp_sample_kernel(const float* __restrict__ x, const float* __restrict__ z, const
           for (int j = 0; j < 4; ++j) d2[i][j] = 0.f;
         for (int f = 0; f < F; ++f) {
           const float il = s_inv_ls[f];
-          float xr[2], xc[4][2];
+          float xr[4], xc[4];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int r = r0 + wrp * 16 + fg + 8 * h;
-            xr[h] = r < T ? xb[static_cast<size_t>(r) * F + f] * il : 0.f;
+          for (int i = 0; i < 4; ++i) {
+            const int r = r0 + ty * 4 + i;
+            xr[i] = r < T ? xb[static_cast<size_t>(r) * F + f] * il : 0.f;
+            const int c = c0 + tx * 4 + i;
+            xc[i] = c < T ? xb[static_cast<size_t>(c) * F + f] * il : 0.f;
           }
 #pragma unroll
-          for (int nt = 0; nt < 4; ++nt)
+          for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int c = c0 + nt * 8 + 2 * ft + e;
-              xc[nt][e] = c < T ? xb[static_cast<size_t>(c) * F + f] * il : 0.f;
-            }
-#pragma unroll
-          for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { const float df = xr[j >> 1] - xc[nt][j & 1]; d2[nt][j] = fmaf(df, df, d2[nt][j]); }
+            for (int j = 0; j < 4; ++j) { const float df = xr[i] - xc[j]; d2[i][j] = fmaf(df, df, d2[i][j]); }
         }
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
+        for (int i = 0; i < 4; ++i) {
+          const int r = r0 + ty * 4 + i;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int tr_ = wrp * 16 + fg + 8 * (j >> 1), tc_ = nt * 8 + 2 * ft + (j & 1);
-            const int r = r0 + tr_, c = c0 + tc_;
+            const int c = c0 + tx * 4 + j;
             float u = 0.f;
             if (r < T && c < T) {
-              u = gp_kernel_value(d2[nt][j], os, kernel_type);
+              u = gp_kernel_value(d2[i][j], os, kernel_type);
               if (r == c) u = os + diag_add;   // k(x,x) = 1 for every supported kernel
-              u -= acc[nt][j];
+              u -= acc[i][j];
             }
-            sU[tr_][tc_] = u;
+            sU[ty * 4 + i][tx * 4 + j] = u;
           }
         }
       }
       __syncthreads();
-      // ---------------------------------------------------------------- diagonal block: chol + inverse in registers (warp 0)
+      // ---------------------------------------------------------------- diagonal block: chol in registers (warp 0)
       if (r0 == c0) {
         if (tid < 32) {
           float row[NB];
@@ -243,54 +202,38 @@ gp_sample_kernel(const float* __restrict__ x, const float* __restrict__ z, const
           }
 #pragma unroll
           for (int c = 0; c < NB; ++c) sL[lane][c] = (c <= lane) ? row[c] : 0.f;
-          // W = L11^-1 by forward substitution, lane = column j of W:  W[i][j] = (delta_ij - sum_{j<=k<i} L[i][k] W[k][j]) / L[i][i]
-          // (row i of L11 is broadcast from the lane that holds it)
-          float wcol[NB];
+          float dg = 1.0f;
 #pragma unroll
-          for (int i = 0; i < NB; ++i) {
-            float acc_w = (i == lane) ? 1.0f : 0.f;
-#pragma unroll
-            for (int k = 0; k < i; ++k) {
-              const float lik = __shfl_sync(0xffffffffu, row[k], i);
-              acc_w = fmaf(-lik, wcol[k], acc_w);
-            }
-            const float lii = __shfl_sync(0xffffffffu, row[i], i);
-            wcol[i] = (i >= lane) ? acc_w / lii : 0.f;
-          }
-#pragma unroll
-          for (int i = 0; i < NB; ++i) sW[i][lane] = wcol[i];
+          for (int c = 0; c < NB; ++c) dg = (c == lane) ? row[c] : dg;
+          sLinv[lane] = 1.0f / dg;
         }
         __syncthreads();
       }
-      // ---------------------------------------------------------------- rows below the diagonal block: V = U W^T (all warps)
-      //   V[r][c] = sum_k U[r][k] W[c][k]:   A(row, k) = sU[16 w + row][k],   B(k, n) = sW[n][k]
-      {
-        float v[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) v[i][j] = 0.f;
-        mma_3xtf32_16x32<NB / 8>(v, &sU[wrp * 16][0], 1, LDU, &sW[0][0], 1, LDU, fg, ft);
-        __syncthreads();                 // every warp has read its U rows before they are overwritten with V
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) sU[wrp * 16 + fg + 8 * (j >> 1)][nt * 8 + 2 * ft + (j & 1)] = v[nt][j];
-      }
-      __syncthreads();
-      // ---------------------------------------------------------------- write the panel rows, y += L[r, panel] . z[panel]
+      // ---------------------------------------------------------------- write the diagonal block / solve the rows below
       if (tid < TR) {
         const int r = r0 + tid;
         if (r < T) {
-          const bool in_diag = (r0 == c0 && tid < NB);
+          float v[NB];
+          if (r0 == c0 && tid < NB) {
+#pragma unroll
+            for (int c = 0; c < NB; ++c) v[c] = sL[tid][c];
+          } else {
+#pragma unroll
+            for (int c = 0; c < NB; ++c) {
+              float a = sU[tid][c];
+#pragma unroll
+              for (int p = 0; p < c; ++p) a = fmaf(-v[p], sL[c][p], a);
+              v[c] = a * sLinv[c];
+            }
+          }
           float dot = 0.f;
 #pragma unroll
-          for (int c = 0; c < NB; ++c) {
-            const float vc = in_diag ? sL[tid][c] : sU[tid][c];
-            dot = fmaf(vc, sz[c], dot);
-            if (c0 + c < T) Lt[static_cast<size_t>(c0 + c) * ldw + r] = vc;     // lanes = consecutive r: coalesced
-          }
+          for (int c = 0; c < NB; ++c) dot = fmaf(v[c], sz[c], dot);
           yb[r] += dot;
+#pragma unroll
+          for (int c = 0; c < NB; ++c) {
+            if (c0 + c < T) Lt[static_cast<size_t>(c0 + c) * ldw + r] = v[c];     // lanes = consecutive r: coalesced
+          }
         }
       }
       __syncthreads();
@@ -298,6 +241,8 @@ gp_sample_kernel(const float* __restrict__ x, const float* __restrict__ z, const
   }
   if (tid == 0) info[b] = s_info;
 }
+
+constexpr int gp_dyn_smem(int tr) { return GP_STAGES * (NB * tr + NB * NB) * static_cast<int>(sizeof(float)); }
 
 }  // namespace pfn
 
@@ -311,13 +256,24 @@ extern "C" int pfn_gp_sample(const float* x, const float* z, const float* ls, co
   PFN_CHECK_ARG(kernel_type >= PFN_KERNEL_RBF && kernel_type <= PFN_KERNEL_MATERN52, "gp_sample: bad kernel type %d", kernel_type);
   PFN_CHECK_ARG((reinterpret_cast<uintptr_t>(work) & 15) == 0, "gp_sample: work buffer must be 16-byte aligned");
   const int ldw = (T + 3) & ~3;
-  constexpr int kDynSmem = GP_STAGES * (NB * LDR + NB * LDC) * static_cast<int>(sizeof(float));
+  // Measured on one B200 (tools/time_kernels.py gp, T = 1000): 512 datasets 9.9 ms with TR = 128 vs 7.8 ms with TR = 64;
+  // 296 datasets 4.46 vs 4.94 ms; 148 datasets 2.94 vs 3.51 ms -> the small tile only once the batch no longer fits one
+  // wave of the large one.  (PFN_GP_TR pins one of them for A/B builds.)
+#ifdef PFN_GP_TR
+  const bool small_tile = PFN_GP_TR == 64;
+#else
+  const bool small_tile = Bn > 2 * num_sms();
+#endif
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   static bool attr_set[64] = {};
   if (first_use_on_device(attr_set)) {
-    PFN_CUDA_OK(cudaFuncSetAttribute(gp_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem));
+    PFN_CUDA_OK(cudaFuncSetAttribute(gp_sample_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, gp_dyn_smem(64)));
+    PFN_CUDA_OK(cudaFuncSetAttribute(gp_sample_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, gp_dyn_smem(128)));
   }
-  gp_sample_kernel<<<Bn, 256, kDynSmem, reinterpret_cast<cudaStream_t>(stream)>>>(x, z, ls, os, noise, jitter, kernel_type, y,
-                                                                         work, info, T, F, ldw);
+  if (small_tile)
+    gp_sample_kernel<64><<<Bn, 128, gp_dyn_smem(64), s>>>(x, z, ls, os, noise, jitter, kernel_type, y, work, info, T, F, ldw);
+  else
+    gp_sample_kernel<128><<<Bn, 256, gp_dyn_smem(128), s>>>(x, z, ls, os, noise, jitter, kernel_type, y, work, info, T, F, ldw);
   PFN_LAUNCH_OK();
   return 0;
 }

@@ -24,6 +24,7 @@ LN_EPS = 1e-5
 # Data-parallel hook (parallel.OverlappedGradReducer): when set, it is called from inside the backward passes as soon as a
 # bucket of parameter gradients is complete in stream order -- `hook(flat_fp32_bucket)` -- so that its all-reduce overlaps the
 # rest of the backward; `GRAD_BUCKET_SYNC()` is called before the gradients are handed to autograd.
+_DELTA_FUSION = os.environ.get("PFN_B200_DELTA_FUSION", "1") != "0"     # A/B knob (tools/ab_env.sh)
 GRAD_BUCKET_HOOK = None
 GRAD_BUCKET_SYNC = None
 
@@ -76,11 +77,12 @@ def _linear_fwd(x, w_c, bias, *, aux=None, epilogue=L.EPI_NONE, want_pre=False, 
     return (y, pre) if want_pre else y
 
 
-def _linear_dgrad(dy, w_c, *, aux=None, epilogue=L.EPI_NONE):
-    """dx = dy @ w_c (+aux | * gelu'(aux)).  dy [M,N], w_c [N,K] read as an MN-major B operand."""
+def _linear_dgrad(dy, w_c, *, aux=None, epilogue=L.EPI_NONE, rowdot=None):
+    """dx = dy @ w_c (+aux | * gelu'(aux) | with rowdot[0][m, k // rowdot[1]] += sum_k dx[m,k] aux[m,k]).
+    dy [M,N], w_c [N,K] read as an MN-major B operand."""
     M, K = dy.shape[0], w_c.shape[1]
     dx = torch.empty(M, K, device=dy.device, dtype=dy.dtype)
-    L.gemm(dy, w_c, dx, b_mn_major=True, aux=aux, epilogue=epilogue, M=M, N=K, K=w_c.shape[0])
+    L.gemm(dy, w_c, dx, b_mn_major=True, aux=aux, epilogue=epilogue, M=M, N=K, K=w_c.shape[0], rowdot=rowdot)
     return dx
 
 
@@ -203,14 +205,22 @@ class EncoderStackFn(torch.autograd.Function):
                 L.dropout(dz1, da, site_seed(drop[0], li, 1), drop[1])
                 L.colsum(da, G["out_b"])
             _linear_wgrad(da, attn, G["out_w"])
-            dattn = _linear_dgrad(da, out_w)
+            tc_attn = L.tc_attention_ok(qkv, dh)
+            fuse_delta = tc_attn and _DELTA_FUSION and L.tc_gemm_ok(da, out_w, attn, attn)
+            if fuse_delta:
+                # delta = rowsum(dO * O) per (token, head) falls out of the out-projection dgrad's epilogue (the thread that
+                # holds a row of dO for one head multiplies it with the O row it reads as `aux`): no separate pass over O and dO
+                delta = torch.zeros(N, nhead, device=dev, dtype=torch.float32)
+                dattn = _linear_dgrad(da, out_w, aux=attn, epilogue=L.EPI_ROWDOT, rowdot=(delta, dh))
+            else:
+                delta = torch.empty_like(lse)
+                dattn = _linear_dgrad(da, out_w)
             del da
             dqkv = torch.empty_like(qkv)
-            delta = torch.empty_like(lse)
-            fused_bias = (not drop) and L.tc_attention_ok(qkv, dh)
+            fused_bias = (not drop) and tc_attn
             L.attention_bwd(qkv, attn, lse, dattn, dqkv, delta, T, B, nhead, dh, sep,
                             drop=(site_seed(drop[0], li, 0), drop[1]) if drop else None,
-                            dq_colsum=G["in_b"][:E] if fused_bias else None)
+                            dq_colsum=G["in_b"][:E] if fused_bias else None, delta_token_major=fuse_delta)
             del dattn, attn, qkv
             if fused_bias:
                 # in-projection bias gradient without re-reading dqkv (1.5 GB per layer at cfg 2): the q third comes out of
