@@ -41,12 +41,14 @@
 namespace pfn {
 
 constexpr int DQ_KS = 4;                                   // K/V block ring depth
+constexpr int DQ_THREADS = AB_THREADS + 32;                // + warp 10: issuer of the dQ-accumulate MMAs
 constexpr int DQ_SMEM_Q = 0;
 constexpr int DQ_SMEM_DO = AB_TILE_BYTES;
 constexpr int DQ_SMEM_KV = 2 * AB_TILE_BYTES;              // stage s: K at +s*32K, V at +16K
 constexpr int DQ_SMEM_OUT = DQ_SMEM_KV + DQ_KS * 2 * AB_BLK_BYTES;   // dQ staging tile, 32 KB
 constexpr int DQ_SMEM_BARS = DQ_SMEM_OUT + AB_TILE_BYTES;
-constexpr int DQ_SMEM = DQ_SMEM_BARS + 512 + 1024;         // + barriers + 1 KB alignment slack
+constexpr int DQ_SMEM_SELF = DQ_SMEM_BARS + 512;           // [2][64] float2: (dS_ii, P_ii) of a diagonal block's rows
+constexpr int DQ_SMEM = DQ_SMEM_SELF + 1024 + 1024;        // + 1 KB alignment slack
 
 constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DQ = 256, TM_Q = 384, TM_DO = 448;
 
@@ -57,17 +59,20 @@ __device__ __forceinline__ uint64_t dq_desc(uint32_t lo) { return (static_cast<u
 __device__ __forceinline__ uint32_t dq_lo_kmajor(uint32_t addr16) { return ((16u >> 4) << 16) | addr16; }
 __device__ __forceinline__ uint32_t dq_lo_mnmajor(uint32_t addr16) { return ((8192u >> 4) << 16) | addr16; }
 
-__global__ void __launch_bounds__(AB_THREADS, 1)
+__global__ void __launch_bounds__(DQ_THREADS, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
                       const __grid_constant__ CUtensorMap tmDO128, const __grid_constant__ CUtensorMap tmDQ,
                       const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1 KB alignment by an OFFSET on the __shared__ symbol (an integer round trip of the pointer makes every access through it a
+  // generic LD.E / ST.E instead of LDS / STS)
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem + DQ_SMEM_Q;
   uint8_t* sDO = smem + DQ_SMEM_DO;
   uint8_t* sKV = smem + DQ_SMEM_KV;
   uint8_t* sOut = smem + DQ_SMEM_OUT;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DQ_SMEM_BARS);
+  float2* sSelf = reinterpret_cast<float2*>(smem + DQ_SMEM_SELF);
   uint64_t* qdo_full = bars + 0;                 // TMA: Q / dO tile landed
   uint64_t* qdo_free = bars + 1;                 // row warps: smem Q / dO tile no longer read
   uint64_t* qt_ready = bars + 2;                 // row warps: Q / dO copied into TMEM
@@ -167,93 +172,84 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
         if (j == jq && w + static_cast<int>(gridDim.x) < p.total_work) load_qdo(w + gridDim.x, tcount + 1);
       }
     }
-  } else if (warp == 1) {
-    // =============================================================== MMA issuer (converged warp, one elected lane issues)
-    // The single issuing thread is the scarce resource: the tcgen05 queue is shallow, so a gap in this warp is tensor-pipe
-    // idle time.  Measured (tools/ubench/mma_gap.cu, clocks per block against a pipe floor of 768): descriptor arithmetic,
-    // tcgen05.commit and tcgen05.fence are free; every poll of an already-complete mbarrier costs ~120 (all 32 lanes
-    // polling) or ~210 (one lane polling, the rest parked at __syncwarp) -- so all lanes poll, and ring positions are
-    // (stage, phase) counters (score buffer = stage & 1: both advance once per block).  A/B on the real kernel: one-lane
-    // polling 2.16 ms vs 1.33 ms; compile-time stage dispatch (4 code copies) 1.44 ms vs 1.33 ms.
+  } else if (warp == 1 || warp == 10) {
+    // =============================================================== MMA issuers (converged warps, one elected lane issues)
+    // TWO issuing warps: warp 1 issues the score batches (S_j, dP_j), warp 10 the dQ-accumulate batches.  With a single
+    // issuer the tcgen05 queue is shallow enough that every issue blocks until the pipe has nearly caught up, so one thread
+    // served, in series, the score issue (~610 clk), the wait for dS, the accumulate issue (~540 clk) and the barrier
+    // polls (~120 clk each on a complete barrier): 1 830 clk per 64-key block against a pipe floor of 768
+    // (profiles/r2_trace_attn_bwd_dq_clock64.txt).  Split, the two issue streams and their polls overlap; the only ordering
+    // the single thread provided implicitly -- the scores of block n+2 overwrite the S / dP buffers whose dS aliases feed
+    // the dQ MMA of block n -- is now the kv_empty barrier of block n (committed behind that MMA), which warp 1 polls.
+    // (tools/ubench/mma_gap.cu: descriptor arithmetic, tcgen05.commit and tcgen05.fence are free; all lanes poll.)
     const uint32_t kv16 = tc::smem_u32(sKV) >> 4;
-    int stage = 0;            // ring position (= score buffer parity) of the block whose SCORES are issued next
-    uint32_t sphase = 0;
-    int astage = 0;           // ring position of the block whose dQ MMA is issued next
-    uint32_t aphase = 0;      // phase of ds_ready[astage & 1]: toggles every second block
-    uint32_t tcount = 0;
     constexpr uint32_t idesc_s = tc::umma_idesc_bf16(128, 64, 0, 0);
     constexpr uint32_t idesc_q = tc::umma_idesc_bf16(128, 128, 0, 1);
-    auto rt_scores = [&](int st) {
-      const uint32_t sb = st & 1;
-      const uint32_t k16 = kv16 + static_cast<uint32_t>(st) * (2 * AB_BLK_BYTES >> 4);
-      const uint32_t v16 = k16 + (AB_BLK_BYTES >> 4);
-      if (tc::elect_one()) {
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          tc::umma_bf16_ts(tmem_base + TM_S + sb * 64, tmem_base + TM_Q + kk * 8,
-                           dq_desc(dq_lo_kmajor(k16 + (kk >> 2) * (8192 >> 4) + (kk & 3) * 2)), idesc_s, kk > 0 ? 1u : 0u);
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          tc::umma_bf16_ts(tmem_base + TM_DP + sb * 64, tmem_base + TM_DO + kk * 8,
-                           dq_desc(dq_lo_kmajor(v16 + (kk >> 2) * (8192 >> 4) + (kk & 3) * 2)), idesc_s, kk > 0 ? 1u : 0u);
-        tc::umma_commit(&s_full[sb]);
-      }
-      __syncwarp();
-    };
-    auto rt_acc = [&](int st, bool accumulate, bool last) {
-      const uint32_t k16 = kv16 + static_cast<uint32_t>(st) * (2 * AB_BLK_BYTES >> 4);
-      if (tc::elect_one()) {
-        const uint32_t a0 = tmem_base + TM_S + (st & 1) * 64;
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          tc::umma_bf16_ts(tmem_base + TM_DQ, a0 + (kk >> 1) * 32 + (kk & 1) * 8,
-                           dq_desc(dq_lo_mnmajor(k16 + kk * (2048 >> 4))), idesc_q, (accumulate || kk > 0) ? 1u : 0u);
-        tc::umma_commit(&kv_empty[st]);
-        if (last) tc::umma_commit(dq_done);
-      }
-      __syncwarp();
-    };
-    // Barriers are probed one batch EARLY: the probe's ~120-clock round trip then overlaps the blocking issue of the batch
-    // in between instead of draining the tensor queue; the spinning wait is only the fallback.
-    bool kv_ok = false;       // early probe result for kv_full[stage] / sphase
-    auto issue_scores = [&]() {
-      if (!kv_ok) tc::mbar_wait(&kv_full[stage], sphase);
-      kv_ok = false;
-      tc::tc_fence_after();
-      rt_scores(stage);
-      if (++stage == DQ_KS) { stage = 0; sphase ^= 1; }
-    };
-    bool first = true;
-    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
-      const int qt = w % p.n_tiles;
-      int dstart[2];
-      const int nb = ab_tile_block_plan(qt * 128, p.sep, p.T, nblk, dstart);
-      if (first) {            // very first block of this CTA: nothing to overlap with yet
-        tc::mbar_wait(qt_ready, 0);
-        tc::tc_fence_after();
-        issue_scores();
-        first = false;
-      }
-      const bool has_next = w + static_cast<int>(gridDim.x) < p.total_work;
-      for (int j = 0; j < nb; ++j) {
-        const bool last = (j + 1 == nb);
-        bool ds_ok = false;
-        if (!last) {
-          ds_ok = tc::mbar_try_wait(&ds_ready[astage & 1], aphase);   // early probe, consumed after the score batch
-          issue_scores();                                             // scores of block j+1 run under the row work of block j
-        }
-        if (!ds_ok) tc::mbar_wait(&ds_ready[astage & 1], aphase);
-        if (j == 0 && tcount > 0) tc::mbar_wait(dq_empty, (tcount - 1) & 1);   // previous tile's dQ read out of TMEM
-        tc::tc_fence_after();
-        if (j + 2 < nb) kv_ok = tc::mbar_try_wait(&kv_full[stage], sphase);   // for the NEXT iteration's score batch
-        rt_acc(astage, j > 0, last);
-        if (astage & 1) aphase ^= 1;
-        if (++astage == DQ_KS) astage = 0;
-        if (last && has_next) {
-          // the row warps copy the next tile's Q / dO into TMEM right after publishing this tile's last dS
-          tc::mbar_wait(qt_ready, (tcount + 1) & 1);
+    int stage = 0;            // ring position (= score buffer parity) of the block this warp handles next
+    uint32_t sphase = 0;      // phase of kv_full[stage] / kv_empty[stage]
+    uint32_t tcount = 0;
+    tc::KernelTrace tr = tc::trace_make(p.trace, p.trace_cap, warp == 1 ? 1 : 10);
+    if (warp == 1) {
+      uint32_t n = 0;         // blocks issued so far
+      int st2 = 0;            // ring position / phase of block n - 2
+      uint32_t ph2 = 0;
+      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
+        const int qt = w % p.n_tiles;
+        int dstart[2];
+        const int nb = ab_tile_block_plan(qt * 128, p.sep, p.T, nblk, dstart);
+        tc::mbar_wait(qt_ready, tcount & 1);          // the row warps have copied this tile's Q / dO into TMEM
+        for (int j = 0; j < nb; ++j, ++n) {
+          tc::mbar_wait(&kv_full[stage], sphase);
+          if (n >= 2) {                                // the dQ MMA of block n-2 no longer reads the dS over this S buffer
+            tc::mbar_wait(&kv_empty[st2], ph2);
+            if (++st2 == DQ_KS) { st2 = 0; ph2 ^= 1; }
+          }
           tc::tc_fence_after();
-          issue_scores();
+          if (lane == 0) DQ_LOG(tr, 11, tcount, j);
+          const uint32_t sb = stage & 1;
+          const uint32_t k16 = kv16 + static_cast<uint32_t>(stage) * (2 * AB_BLK_BYTES >> 4);
+          const uint32_t v16 = k16 + (AB_BLK_BYTES >> 4);
+          if (tc::elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              tc::umma_bf16_ts(tmem_base + TM_S + sb * 64, tmem_base + TM_Q + kk * 8,
+                               dq_desc(dq_lo_kmajor(k16 + (kk >> 2) * (8192 >> 4) + (kk & 3) * 2)), idesc_s, kk > 0 ? 1u : 0u);
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              tc::umma_bf16_ts(tmem_base + TM_DP + sb * 64, tmem_base + TM_DO + kk * 8,
+                               dq_desc(dq_lo_kmajor(v16 + (kk >> 2) * (8192 >> 4) + (kk & 3) * 2)), idesc_s, kk > 0 ? 1u : 0u);
+            tc::umma_commit(&s_full[sb]);
+          }
+          __syncwarp();
+          if (lane == 0) DQ_LOG(tr, 14, tcount, j);
+          if (++stage == DQ_KS) { stage = 0; sphase ^= 1; }
+        }
+      }
+    } else {
+      uint32_t aphase = 0;    // phase of ds_ready[stage & 1]: toggles every second block
+      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
+        const int qt = w % p.n_tiles;
+        int dstart[2];
+        const int nb = ab_tile_block_plan(qt * 128, p.sep, p.T, nblk, dstart);
+        for (int j = 0; j < nb; ++j) {
+          tc::mbar_wait(&ds_ready[stage & 1], aphase);
+          if (j == 0 && tcount > 0) tc::mbar_wait(dq_empty, (tcount - 1) & 1);   // previous tile's dQ read out of TMEM
+          tc::tc_fence_after();
+          if (lane == 0) DQ_LOG(tr, 12, tcount, j);
+          const uint32_t k16 = kv16 + static_cast<uint32_t>(stage) * (2 * AB_BLK_BYTES >> 4);
+          if (tc::elect_one()) {
+            const uint32_t a0 = tmem_base + TM_S + (stage & 1) * 64;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              tc::umma_bf16_ts(tmem_base + TM_DQ, a0 + (kk >> 1) * 32 + (kk & 1) * 8,
+                               dq_desc(dq_lo_mnmajor(k16 + kk * (2048 >> 4))), idesc_q, (j > 0 || kk > 0) ? 1u : 0u);
+            tc::umma_commit(&kv_empty[stage]);
+            if (j + 1 == nb) tc::umma_commit(dq_done);
+          }
+          __syncwarp();
+          if (lane == 0) DQ_LOG(tr, 13, tcount, j);
+          if (stage & 1) aphase ^= 1;
+          if (++stage == DQ_KS) { stage = 0; sphase ^= 1; }
         }
       }
     }
@@ -328,9 +324,12 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
         const bool diag = j < nd;
         const int kmax = diag ? 0 : p.sep - (j - nd) * 64;
         uint32_t s[32], dp[32], pk[16];
+        float dself = 0.f, pself = 0.f;     // diagonal block: dS_ii and P_ii (x dropout factor) of this thread's own key
+        bool has_self = false;
         tc::tmem_ld_32x32b_x32(tmem_base + lane_off + TM_S + buf * 64 + half * 32, s);
         tc::tmem_ld_32x32b_x32(tmem_base + lane_off + TM_DP + buf * 64 + half * 32, dp);
         tc::tmem_ld_wait();
+        if (lane == 0) DQ_LOG(tr, 25 + 100 * warp, tcount, j);
         if (!diag && p.drop_thr > 0) {
           // dropout on the probabilities (csrc/dropout.cuh): dS = P (m dP / (1 - p) - delta) scale, keep bit of key j = byte j & 3
           // of the hash of (row id (b*H + h)*T + i, j >> 2); covers full and partial dense blocks
@@ -382,26 +381,23 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
             sv = (c == cl) ? __uint_as_float(s[c]) : sv;
             dv = (c == cl) ? __uint_as_float(dp[c]) : dv;
           }
-          float dself = 0.f;
           if (cl >= 0) {
-            // the diagonal key is attended by this row only: dK_i = dS_ii q_i and dV_i = P_ii dO_i are complete.
-            // Q / dO rows are read back from the (still live) swizzled smem tiles.
+            // the diagonal key is attended by this row only: dK_i = dS_ii q_i and dV_i = P_ii dO_i are complete (written
+            // below, after dS has been published)
             const float pii = tc::fast_exp2(fmaf(sv, p.scale_log2, -lse2));
             float mk = 1.f;                                 // dropout keep factor of the diagonal key (column i of row i)
             if (p.drop_thr > 0) mk = drop_keep(p.drop_seed, static_cast<uint32_t>(bh) * p.T + i, static_cast<uint32_t>(i), p.drop_thr) ? drop_scale(p.drop_thr) : 0.f;
             dself = pii * fmaf(dv * mk, p.scale, -dls);
-            const size_t tokq = p.batch_major ? static_cast<size_t>(b) * p.T + i : static_cast<size_t>(i) * p.B + b;
-            __nv_bfloat16* dkv_out = p.dqkv + tokq * p.ld_dqkv + h * AB_DH;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-              float qq[32], dd[32];
-              ab_load32_swz(sQ, row, c * 32, qq);
-              ab_load32_swz(sDO, row, c * 32, dd);
-#pragma unroll
-              for (int e = 0; e < 32; ++e) { qq[e] *= dself; dd[e] *= pii * mk; }
-              ab_store32(dkv_out + E + c * 32, qq);
-              ab_store32(dkv_out + 2 * E + c * 32, dd);
-            }
+            pself = pii * mk;
+            has_self = true;
+          }
+          {
+            // every row of this 64-row diagonal block has one owner thread (the half whose 32 columns hold the row's own
+            // key); it leaves (dS_ii, P_ii) -- or a NaN marker for a row without a diagonal key -- for the warps that write
+            // dK_i / dV_i below
+            const int c64 = i0 + row - dstart[j];
+            if (c64 >= 0 && c64 < 64 && (c64 >> 5) == half)
+              sSelf[(j & 1) * 64 + c64] = make_float2(has_self ? dself : __int_as_float(0x7fc00000), pself);
           }
           const uint32_t lo = tc::pack_bf16x2(dself, 0.f), hi = tc::pack_bf16x2(0.f, dself);
           const int cw = cl >> 1;                         // -1 >> 1 == -1: matches nothing
@@ -409,11 +405,43 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
 #pragma unroll
           for (int c = 0; c < 16; ++c) pk[c] = (c == cw) ? word : 0u;
         }
+        if (lane == 0) DQ_LOG(tr, 26 + 100 * warp, tcount, j);
         tc::tmem_st_32x32b_x16(tmem_base + lane_off + TM_S + buf * 64 + half * 32, pk);
         tc::tmem_st_wait();
         tc::tc_fence_before();
         tc::mbar_arrive_warp(&ds_ready[buf]);
         if (lane == 0) DQ_LOG(tr, 21 + 100 * warp, tcount, j);
+        if (diag) {
+          // dK_i = dS_ii q_i, dV_i = P_ii dO_i for the 64 rows of this diagonal block, AFTER dS went out, shared by all 8
+          // row warps (8 rows each).  A warp writes one row per step: lanes 0..15 the 256-byte dK row, lanes 16..31 the dV
+          // row (16 bytes each, read back from the still-live swizzled smem Q / dO tiles) -- two fully used 256-byte
+          // segments per store instruction.  (One thread per row wrote 32 half-used sectors per instruction, only the 2
+          // warps owning the block's rows worked, and the tile stood still for ~7 000 clocks per diagonal block:
+          // profiles/r2_trace_attn_bwd_dq_clock64.txt.)
+          asm volatile("bar.sync 1, 256;" ::: "memory");          // sSelf of this block complete
+          const int which = lane >> 4, u = lane & 15;
+          const uint8_t* tile = (which ? sDO : sQ) + (u >> 3) * 16384;
+          const int rbase = dstart[j] - i0;                        // tile row of the block's first row (0 or 64)
+#pragma unroll
+          for (int r8 = 0; r8 < 8; ++r8) {
+            const int c64 = (warp - 2) * 8 + r8;
+            const float2 sp = sSelf[(j & 1) * 64 + c64];           // broadcast
+            if (sp.x == sp.x) {                                    // warp-uniform: the row has a diagonal key
+              const float f = which ? sp.y : sp.x;
+              const int rr = rbase + c64;
+              const int ii = i0 + rr;
+              const uint4 raw = *reinterpret_cast<const uint4*>(tile + rr * 128 + (((u & 7) ^ (rr & 7)) << 4));
+              const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&raw);
+              uint4 o;
+              float2 t = __bfloat1622float2(hh[0]); o.x = tc::pack_bf16x2(t.x * f, t.y * f);
+              t = __bfloat1622float2(hh[1]); o.y = tc::pack_bf16x2(t.x * f, t.y * f);
+              t = __bfloat1622float2(hh[2]); o.z = tc::pack_bf16x2(t.x * f, t.y * f);
+              t = __bfloat1622float2(hh[3]); o.w = tc::pack_bf16x2(t.x * f, t.y * f);
+              const size_t tokq = p.batch_major ? static_cast<size_t>(b) * p.T + ii : static_cast<size_t>(ii) * p.B + b;
+              *reinterpret_cast<uint4*>(p.dqkv + tokq * p.ld_dqkv + (which ? 2 * E : E) + h * AB_DH + u * 8) = o;
+            }
+          }
+        }
         if (j + 1 == nd) tc::mbar_arrive_warp(qdo_free);     // last diagonal block: smem Q / dO rows no longer needed
         buf ^= 1;
         if (buf == 0) bphase ^= 1;
@@ -512,7 +540,7 @@ int launch_attn_bwd_dq(const AttnBwdParams& p_in, const pfn_attn_desc* d, cudaSt
   if (first_use_on_device(attr_set))
     PFN_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
   const int grid = num_sms() < p.total_work ? num_sms() : p.total_work;
-  attn_bwd_dq_tc_kernel<<<grid, AB_THREADS, DQ_SMEM, stream>>>(tmQKV128, tmQKV64, tmDO128, tmDQ, p);
+  attn_bwd_dq_tc_kernel<<<grid, DQ_THREADS, DQ_SMEM, stream>>>(tmQKV128, tmQKV64, tmDO128, tmDQ, p);
   PFN_LAUNCH_OK();
   return 0;
 }

@@ -69,11 +69,13 @@ attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ out, int ld_out, const _
 // =====================================================================================================================
 // Kernel 2: dK, dV of the train keys
 // =====================================================================================================================
-__global__ void __launch_bounds__(AB_THREADS, 1)
+__global__ void __launch_bounds__(AB_THREADS + 32, 1)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
                        const __grid_constant__ CUtensorMap tmDO64, const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1 KB alignment by an OFFSET on the __shared__ symbol (an integer round trip of the pointer makes every access through it a
+  // generic LD.E / ST.E instead of LDS / STS)
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sK = smem;
   uint8_t* sV = smem + AB_TILE_BYTES;
   uint8_t* sQD = smem + 2 * AB_TILE_BYTES;               // stage s: Q block at +s*32K, dO block at +16K
@@ -167,52 +169,52 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
     }
   } else if (warp == 1) {
     {
-      // MMA issuer.  Ring positions are (stage, phase) counters and every barrier is probed one batch early: a poll of an
-      // already-complete mbarrier costs the single issuing thread ~120 clocks of tensor-pipe idle time when the shallow
-      // tcgen05 queue has drained (tools/ubench/mma_gap.cu), so the probe's round trip is put under the blocking issue of
-      // the batch in between.
+      // Score issuer (S^T, dP^T of every 64-row block).  The accumulate MMAs are issued by warp 10: with a single issuing
+      // thread the score issue, the wait for P^T / dS^T, the accumulate issue and the barrier polls were served in series
+      // (see attention_bwd_dq.cu); nothing orders the two streams beyond the barriers that already exist (s_consumed guards
+      // the single fp32 score buffer, pd_free the bf16 operand buffers, qd_empty the Q / dO ring).
       const uint32_t k_addr = tc::smem_u32(sK), v_addr = tc::smem_u32(sV);
       const uint32_t qd_addr0 = tc::smem_u32(sQD);
-      int sst = 0;               // ring stage of the block whose SCORES are issued next
+      int sst = 0;               // ring stage of the block whose scores are issued next
       uint32_t sph = 0;
-      int ast = 0;               // ring stage of the block whose dV / dK MMAs are issued next
       uint32_t nsc = 0;          // score batches issued so far
-      uint32_t g = 0, tcount = 0;
-      bool qd_ok = false, sc_ok = false;     // early probe results for the NEXT score batch
-      auto issue_scores = [&]() {
-        const uint32_t q_addr = qd_addr0 + static_cast<uint32_t>(sst) * (2 * AB_BLK_BYTES);
-        if (!qd_ok) tc::mbar_wait(&qd_full[sst], sph);
-        if (nsc > 0 && !sc_ok) tc::mbar_wait(s_consumed, (nsc - 1) & 1);      // the previous block's scores are in registers
-        qd_ok = false; sc_ok = false;
-        tc::tc_fence_after();
-        if (tc::elect_one()) {
-          ab_mma_ss_128x64(tmem_base, k_addr, q_addr);                             // S^T  = K Q^T
-          ab_mma_ss_128x64(tmem_base + 64, v_addr, q_addr + AB_BLK_BYTES);         // dP^T = V dO^T
-          tc::umma_commit(st_full);
-        }
-        __syncwarp();
-        ++nsc;
-        if (++sst == AB_KS) { sst = 0; sph ^= 1; }
-      };
+      uint32_t tcount = 0;
+      tc::KernelTrace tr = tc::trace_make(p.trace, p.trace_cap, 1);
       for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
         tc::mbar_wait(kv_full, tcount & 1);
-        issue_scores();
+        for (int i = 0; i < nq; ++i) {
+          const uint32_t q_addr = qd_addr0 + static_cast<uint32_t>(sst) * (2 * AB_BLK_BYTES);
+          tc::mbar_wait(&qd_full[sst], sph);
+          if (nsc > 0) tc::mbar_wait(s_consumed, (nsc - 1) & 1);      // the previous block's scores are in registers
+          tc::tc_fence_after();
+          if (lane == 0) tr.log(11, tcount, i);
+          if (tc::elect_one()) {
+            ab_mma_ss_128x64(tmem_base, k_addr, q_addr);                             // S^T  = K Q^T
+            ab_mma_ss_128x64(tmem_base + 64, v_addr, q_addr + AB_BLK_BYTES);         // dP^T = V dO^T
+            tc::umma_commit(st_full);
+            if (i + 1 == nq) tc::umma_commit(kv_empty);                              // K / V tile no longer read
+          }
+          __syncwarp();
+          if (lane == 0) tr.log(14, tcount, i);
+          ++nsc;
+          if (++sst == AB_KS) { sst = 0; sph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 10) {
+    {
+      // Accumulate issuer: dV += P^T dO_i, dK += dS^T Q_i
+      const uint32_t qd_addr0 = tc::smem_u32(sQD);
+      int ast = 0;
+      uint32_t g = 0, tcount = 0;
+      tc::KernelTrace tr = tc::trace_make(p.trace, p.trace_cap, 10);
+      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
         for (int i = 0; i < nq; ++i, ++g) {
           const uint32_t buf = g & 1;
-          bool pds_ok = false;
-          if (i + 1 < nq) {
-            pds_ok = tc::mbar_try_wait(&pds_ready[buf], (g >> 1) & 1);     // early probe, consumed after the score batch
-            issue_scores();
-          } else {
-            if (tc::elect_one()) tc::umma_commit(kv_empty);
-            __syncwarp();
-          }
-          if (!pds_ok) tc::mbar_wait(&pds_ready[buf], (g >> 1) & 1);
+          tc::mbar_wait(&pds_ready[buf], (g >> 1) & 1);
           if (i == 0) tc::mbar_wait(acc_empty, (tcount & 1) ^ 1);
           tc::tc_fence_after();
-          // probes for the next score batch (this tile's block i+2, or the next tile's block 0: same ring, same counters)
-          qd_ok = tc::mbar_try_wait(&qd_full[sst], sph);
-          sc_ok = nsc > 0 && tc::mbar_try_wait(s_consumed, (nsc - 1) & 1);
+          if (lane == 0) tr.log(12, tcount, i);
           const uint32_t q_addr = qd_addr0 + static_cast<uint32_t>(ast) * (2 * AB_BLK_BYTES);
           if (tc::elect_one()) {
             ab_mma_ts_128x128(tmem_base + 256, tmem_base + 128 + buf * 64, q_addr + AB_BLK_BYTES, i > 0);   // dV += P^T dO
@@ -222,6 +224,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
             if (i + 1 == nq) tc::umma_commit(acc_done);    // one phase per tile
           }
           __syncwarp();
+          if (lane == 0) tr.log(13, tcount, i);
           if (++ast == AB_KS) ast = 0;
         }
       }
@@ -273,6 +276,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
           tc::tmem_ld_32x32b_x32(tmem_base + lane_off + half * 32, s);
           tc::tmem_ld_32x32b_x32(tmem_base + lane_off + 64 + half * 32, dp);
           tc::tmem_ld_wait();
+          if (lane == 0) tr.log(25 + 100 * warp, tcount, i);
           tc::tc_fence_before();
           tc::mbar_arrive_warp(s_consumed);          // the score buffer may be overwritten by the next block's MMAs
           if (key_ok && p.drop_thr == 0) {
@@ -316,7 +320,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
 #pragma unroll
             for (int c = 0; c < 16; ++c) { pkp[c] = 0u; pkd[c] = 0u; }
           }
+          if (lane == 0) tr.log(26 + 100 * warp, tcount, i);
           tc::mbar_wait(&pd_free[buf], ((g >> 1) & 1) ^ 1);      // accumulate MMAs of block g-2 no longer read this buffer
+          if (lane == 0) tr.log(27 + 100 * warp, tcount, i);
           tc::tc_fence_after();
           tc::tmem_st_32x32b_x16(tmem_base + lane_off + 128 + buf * 64 + half * 16, pkp);
           tc::tmem_st_32x32b_x16(tmem_base + lane_off + 160 + buf * 64 + half * 16, pkd);
@@ -328,6 +334,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
         if (lane == 0) tr.log(21 + 100 * warp, tcount, i);
       }
       tc::mbar_wait(acc_done, tcount & 1);                    // committed once per tile, after its last dV/dK MMA
+      if (lane == 0) tr.log(22 + 100 * warp, tcount, 0);
       tc::tc_fence_after();
       const bool store_ok = j < p.sep && j < p.T;
       const size_t krow = p.batch_major ? static_cast<size_t>(b) * p.T + (store_ok ? j : 0) : static_cast<size_t>(store_ok ? j : 0) * p.B + b;
@@ -345,6 +352,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
       }
       tc::tc_fence_before();
       tc::mbar_arrive_warp(acc_empty);
+      if (lane == 0) tr.log(23 + 100 * warp, tcount, 0);
     }
   }
 
@@ -420,7 +428,7 @@ extern "C" int pfn_attention_bwd_tc(const pfn_attn_desc* d, void* stream) {
     p.total_work = p.n_tiles * d->B * d->H;
     int grid = num_sms() < p.total_work ? num_sms() : p.total_work;
     p.trace = g_trace_which == 2 ? g_trace_ptr : nullptr;
-    attn_bwd_dkv_tc_kernel<<<grid, AB_THREADS, AB_SMEM, s>>>(tmQKV128, tmQKV64, tmDO64, p);
+    attn_bwd_dkv_tc_kernel<<<grid, AB_THREADS + 32, AB_SMEM, s>>>(tmQKV128, tmQKV64, tmDO64, p);
     p.trace = nullptr;
     PFN_LAUNCH_OK();
   }

@@ -98,7 +98,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   using Cfg = GemmCfg<BLOCK_N, CTA2>;
   const int STAGES = p.tma_store ? Cfg::kStagesStaged : Cfg::kStagesMax;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1 KB alignment by an OFFSET on the __shared__ symbol (an integer round trip of the pointer makes every access through it a
+  // generic LD.E / ST.E instead of LDS / STS)
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * Cfg::kABytes;
   uint8_t* sOut = smem + STAGES * (Cfg::kABytes + Cfg::kBBytes);      // only used when p.tma_store
