@@ -2,6 +2,8 @@
 // One warp per token row, 16-byte vector accesses, fp32 statistics; column reductions (dgamma, dbeta, bias
 // gradients) are accumulated per lane across the rows a warp owns, combined per CTA in shared memory and
 // flushed with one atomicAdd per column per CTA.
+#include <type_traits>
+
 #include "common.cuh"
 #include "../../include/pfn_b200.h"
 
@@ -330,6 +332,134 @@ layernorm_bwd_kernel(const T* __restrict__ dh, int lddh, const T* __restrict__ z
   }
 }
 
+// bf16 LayerNorm backward with the two input rows staged through a per-warp cp.async ring in shared memory: the bytes in
+// flight no longer live in registers (the register-prefetch kernel above holds 3 rows x 2 tensors = 6 KB per warp, 48 KB per
+// SM, and reaches ~4.0 TB/s), so a warp keeps LN_RING_D - 1 rows (x 2 tensors x 1 KB at E = 512) outstanding.
+#ifndef PFN_LN_RING_D
+#define PFN_LN_RING_D 8
+#endif
+constexpr int LN_RING_D = PFN_LN_RING_D;
+__device__ __forceinline__ void ln_cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))), "l"(gsrc) : "memory");
+}
+template <int NCH>
+__global__ void __launch_bounds__(256, 1)
+layernorm_bwd_ring_kernel(const __nv_bfloat16* __restrict__ dh, int lddh, const __nv_bfloat16* __restrict__ z, int ldz,
+                          const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                          const float* __restrict__ gamma, __nv_bfloat16* __restrict__ dz, int lddz,
+                          float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ colsum_out, int rows, int E) {
+  extern __shared__ __align__(16) uint8_t ln_smem[];
+  constexpr int ROWB = NCH * 512;                    // bytes of one staged row of one tensor (NCH x 32 lanes x 16 B)
+  float* sred = reinterpret_cast<float*>(ln_smem);   // [3][E]
+  const int lane = threadIdx.x & 31;
+  const int warp_in_cta = threadIdx.x >> 5;
+  const int warps_per_cta = blockDim.x >> 5;
+  uint8_t* ring = ln_smem + ((3 * E * 4 + 15) & ~15) + static_cast<size_t>(warp_in_cta) * LN_RING_D * 2 * ROWB;
+  const int warp = blockIdx.x * warps_per_cta + warp_in_cta;
+  const int nwarps = gridDim.x * warps_per_cta;
+  const float inv_e = 1.0f / static_cast<float>(E);
+  for (int i = threadIdx.x; i < 3 * E; i += blockDim.x) sred[i] = 0.f;
+  __syncthreads();
+
+  float ag[NCH][8], ab[NCH][8], ac[NCH][8], gm[NCH][8];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { ag[c][i] = 0.f; ab[c][i] = 0.f; ac[c][i] = 0.f; gm[c][i] = 0.f; }
+    const int col = (c * 32 + lane) * 8;
+    if (col < E) load8<float>(gamma + col, gm[c]);
+  }
+  auto issue = [&](int r, int slot) {
+    if (r < rows) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int col = (c * 32 + lane) * 8;
+        if (col < E) {
+          ln_cp_async16(ring + (slot * 2 + 0) * ROWB + (c * 32 + lane) * 16, dh + static_cast<size_t>(r) * lddh + col);
+          ln_cp_async16(ring + (slot * 2 + 1) * ROWB + (c * 32 + lane) * 16, z + static_cast<size_t>(r) * ldz + col);
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+#pragma unroll
+  for (int k = 0; k < LN_RING_D - 1; ++k) issue(warp + k * nwarps, k);
+  float m_l = 0.f, s_l = 0.f;         // statistics of rows it .. it + 31 of this warp, one per lane
+  int it = 0;
+  for (int row = warp; row < rows; row += nwarps, ++it) {
+    if ((it & 31) == 0) {
+      const long long r = static_cast<long long>(row) + static_cast<long long>(lane) * nwarps;
+      m_l = r < rows ? __ldg(mean_in + r) : 0.f;
+      s_l = r < rows ? __ldg(rstd_in + r) : 0.f;
+    }
+    const float mean = __shfl_sync(0xffffffffu, m_l, it & 31), rstd = __shfl_sync(0xffffffffu, s_l, it & 31);
+    asm volatile("cp.async.wait_group %0;" ::"n"(LN_RING_D - 2) : "memory");
+    __syncwarp();                       // this row has landed for every lane; every lane is done with the slot refilled next
+    const int slot = it % LN_RING_D;
+    Raw8<__nv_bfloat16> cd[NCH], cz[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      cd[c].a = *reinterpret_cast<const uint4*>(ring + (slot * 2 + 0) * ROWB + (c * 32 + lane) * 16);
+      cz[c].a = *reinterpret_cast<const uint4*>(ring + (slot * 2 + 1) * ROWB + (c * 32 + lane) * 16);
+    }
+    issue(row + (LN_RING_D - 1) * nwarps, (it + LN_RING_D - 1) % LN_RING_D);
+    float xh[NCH][8], g[NCH][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int col = (c * 32 + lane) * 8;
+      if (col < E) {
+        float d[8], zz[8];
+        unpack8(cd[c], d);
+        unpack8(cz[c], zz);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          xh[c][i] = (zz[i] - mean) * rstd;
+          g[c][i] = d[i] * gm[c][i];
+          s1 += g[c][i];
+          s2 = fmaf(g[c][i], xh[c][i], s2);
+          ag[c][i] = fmaf(d[i], xh[c][i], ag[c][i]);
+          ab[c][i] += d[i];
+        }
+      }
+    }
+    s1 = warp_sum(s1) * inv_e;
+    s2 = warp_sum(s2) * inv_e;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int col = (c * 32 + lane) * 8;
+      if (col < E) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          o[i] = rstd * (g[c][i] - s1 - xh[c][i] * s2);
+          ac[c][i] += o[i];
+        }
+        store8<__nv_bfloat16>(dz + static_cast<size_t>(row) * lddz + col, o);
+      }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int col = (c * 32 + lane) * 8;
+    if (col < E) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        atomicAdd(&sred[col + i], ag[c][i]);
+        atomicAdd(&sred[E + col + i], ab[c][i]);
+        atomicAdd(&sred[2 * E + col + i], ac[c][i]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < E; i += blockDim.x) {
+    if (dgamma != nullptr) atomicAdd(&dgamma[i], sred[i]);
+    if (dbeta != nullptr) atomicAdd(&dbeta[i], sred[E + i]);
+    if (colsum_out != nullptr) atomicAdd(&colsum_out[i], sred[2 * E + i]);
+  }
+}
+
 // Generic (any E) fallbacks: one warp per row, scalar accesses, re-reading the row from cache.
 template <typename T>
 __global__ void layernorm_fwd_generic(const T* z, int ldz, const float* gamma, const float* beta, T* h, int ldh,
@@ -533,6 +663,23 @@ static int layernorm_bwd_dispatch(const void* dh, int lddh, const void* z, int l
   int grid = (rows + warps - 1) / warps;
   const int max_grid = num_sms() * 4;
   if (grid > max_grid) grid = max_grid;
+#ifndef PFN_LN_BWD_NO_RING
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    if (vec && E > 256 && E <= 512) {
+      // one persistent CTA per SM, the rows staged through the per-warp cp.async rings
+      constexpr int NCH = 2;
+      const size_t smem = ((3 * static_cast<size_t>(E) * 4 + 15) & ~size_t(15)) + static_cast<size_t>(warps) * LN_RING_D * 2 * NCH * 512;
+      static bool attr_set[64] = {};
+      if (first_use_on_device(attr_set))
+        PFN_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd_ring_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      int g1 = num_sms();
+      if (g1 > (rows + warps - 1) / warps) g1 = (rows + warps - 1) / warps;
+      layernorm_bwd_ring_kernel<NCH><<<g1, 256, smem, s>>>(dhp, lddh, zp, ldz, mean, rstd, gamma, dzp, lddz, dgamma, dbeta, colsum_out, rows, E);
+      PFN_LAUNCH_OK();
+      return 0;
+    }
+  }
+#endif
   if (vec) {
     const size_t smem = 3 * static_cast<size_t>(E) * sizeof(float);
     if (E <= 256) layernorm_bwd_kernel<T, 1><<<grid, 256, smem, s>>>(dhp, lddh, zp, ldz, mean, rstd, gamma, dzp, lddz, dgamma, dbeta, colsum_out, rows, E);

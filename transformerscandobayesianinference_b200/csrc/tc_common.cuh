@@ -119,6 +119,16 @@ __device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
   if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
 }
 
+// Waits of the ROW warps (8-16 warps that all wait for the same barrier at about the same time): with every lane of every
+// warp probing, the probes of one barrier word queue up behind each other; PFN_ROW_POLL_ONE lets lane 0 probe for its warp.
+__device__ __forceinline__ void mbar_wait_rows(uint64_t* bar, uint32_t parity) {
+#ifdef PFN_ROW_POLL_ONE
+  mbar_wait_warp(bar, parity);
+#else
+  mbar_wait(bar, parity);
+#endif
+}
+
 // generic-proxy smem writes -> visible to the async proxy (TMA / UMMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -253,6 +263,12 @@ __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_
       ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
       "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&v)[8]) {
+  __syncwarp();
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
 }
 __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&v)[32]) {
   __syncwarp();   // .sync.aligned: the warp must be converged (callers may come out of divergent code)
