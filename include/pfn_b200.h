@@ -144,6 +144,28 @@ int pfn_dropout(const void* x, int ldx, const void* residual, int ldr, void* out
                 uint32_t seed, int thr, void* stream);
 int pfn_dropout_keep_mask(uint8_t* out, int rows, int cols, uint32_t seed, int thr, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Optimizer step of the training inner loop (reference train.py:94-97):
+ *     torch.nn.utils.clip_grad_norm_(model.parameters(), max_grad_norm);  optimizer.step()      [torch.optim.Adam]
+ * over ALL parameter tensors in two launches.  `table` (DEVICE memory, n_tensors entries) names, per tensor, the fp32
+ * parameter, its gradient, the two Adam moments and -- optionally -- a bf16 copy of the parameter that is rewritten with the
+ * updated value (the operand the next step's GEMMs read).  `chunk_start` (DEVICE, n_tensors + 1 ints) holds the prefix sums
+ * of ceil(n / pfn_adam_chunk_elems()) per tensor; n_chunks = chunk_start[n_tensors].  `step` is the 1-based step count of
+ * the bias corrections; max_grad_norm <= 0 skips the clipping; weight_decay is torch.optim.Adam's L2 term.
+ * norm_sq (DEVICE, 1 float) receives the squared total gradient norm BEFORE clipping.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pfn_adam_tensor {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  void* p_bf16;            /* NULL = none */
+  long long n;
+} pfn_adam_tensor;
+int pfn_adam_chunk_elems(void);
+int pfn_adam_step(const pfn_adam_tensor* table, const int* chunk_start, int n_tensors, int n_chunks, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, float max_grad_norm, int step, float* norm_sq, void* stream);
+
 /* column sums: out[n] += sum_m X[m,n]   (bias gradients; torch autograd of addmm bias) */
 int pfn_colsum(const void* X, int ld, int dtype, float* out, int rows, int N, void* stream);
 

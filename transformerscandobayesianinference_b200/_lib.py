@@ -58,6 +58,7 @@ EXPORTED_SYMBOLS = [
     "pfn_bar_nll_fwd", "pfn_bar_nll_bwd", "pfn_bar_bucket_idx",
     "pfn_gp_sample",
     "pfn_dropout", "pfn_dropout_keep_mask",
+    "pfn_adam_step", "pfn_adam_chunk_elems",
 ]
 
 _lib = None
@@ -422,6 +423,23 @@ def dropout_keep_mask(out, seed, thr):
     require_cuda(out)
     rows, cols = out.shape
     check(load().pfn_dropout_keep_mask(ptr(out), rows, cols, int(seed) & 0xFFFFFFFF, int(thr), stream_ptr()), "pfn_dropout_keep_mask")
+
+
+def adam_chunk_elems():
+    return int(load().pfn_adam_chunk_elems())
+
+
+@_guarded
+def adam_step(table, chunk_start, n_tensors, n_chunks, lr, beta1, beta2, eps, weight_decay, max_grad_norm, step, norm_sq):
+    """Clip (max_grad_norm > 0) + Adam update of every tensor of the device-resident pointer table (optim.FusedClipAdam)."""
+    _count(2 if max_grad_norm > 0 else 1)
+    require_cuda(table, chunk_start, norm_sq)
+    c_float = ctypes.c_float
+    fn = load().pfn_adam_step
+    fn.argtypes = [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_float, c_int, c_void_p,
+                   c_void_p]
+    check(fn(ptr(table), ptr(chunk_start), int(n_tensors), int(n_chunks), float(lr), float(beta1), float(beta2), float(eps),
+             float(weight_decay), float(max_grad_norm), int(step), ptr(norm_sq), stream_ptr()), "pfn_adam_step")
 
 
 @_guarded

@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(PKG, "libpfn_b200.so")
 
 SOURCES = [
     "runtime.cu",
+    "optimizer.cu",
     "gemm_tc.cu",
     "gemm_simt.cu",
     "rowwise.cu",

@@ -64,8 +64,10 @@ def site_seed(seed, layer, site):
 
 
 def _cast(w, dtype):
-    w = w.detach()
-    return w.contiguous() if w.dtype == dtype else w.to(dtype).contiguous()
+    """Operand copy of a weight in the activation dtype: the optimizer's bf16 shadow (optim.FusedClipAdam rewrites it inside
+    the update kernel) when it mirrors the current version of the parameter, else a cast."""
+    from .optim import cast_weight
+    return cast_weight(w, dtype)
 
 
 def _linear_fwd(x, w_c, bias, *, aux=None, epilogue=L.EPI_NONE, want_pre=False, out_dtype=None):

@@ -11,6 +11,7 @@ optimizer step (parallel.py).
 public path, not a re-implementation of it.
 """
 import inspect
+import os
 import time
 
 import numpy as np
@@ -108,7 +109,12 @@ class Trainer:
         if lr is None:
             lr = get_openai_lr(model)
             print(f"Using OpenAI max lr of {lr}.")
-        self.optimizer = torch.optim.Adam(model.parameters(), lr=lr, **({'fused': True} if on_cuda else {}))
+        # reference train.py:55 torch.optim.Adam + :94 clip_grad_norm_(1.): on CUDA one fused clip + update (optim.py)
+        if on_cuda and os.environ.get("PFN_B200_FUSED_ADAM", "1") != "0":       # (knob for A/B runs)
+            from .optim import FusedClipAdam
+            self.optimizer = FusedClipAdam(model.parameters(), lr=lr, max_grad_norm=1.)
+        else:
+            self.optimizer = torch.optim.Adam(model.parameters(), lr=lr, **({'fused': True} if on_cuda else {}))
         self.scheduler = scheduler(self.optimizer, warmup_epochs, epochs)
         self.params = [p for p in model.parameters() if p.requires_grad]
         self._micro = 0
@@ -155,7 +161,8 @@ class Trainer:
                 self.reducer.finish(self.params)
             else:
                 parallel.allreduce_gradients(self.params)
-            torch.nn.utils.clip_grad_norm_(model.parameters(), 1.)
+            if not getattr(self.optimizer, "max_grad_norm", 0):          # FusedClipAdam clips inside its step
+                torch.nn.utils.clip_grad_norm_(model.parameters(), 1.)
             self.optimizer.step()
             self.optimizer.zero_grad()
         return loss, losses
