@@ -27,7 +27,7 @@ extern "C" {
 #define PFN_B200_VERSION 1
 
 enum { PFN_F32 = 0, PFN_BF16 = 1 };
-enum { PFN_EPI_NONE = 0, PFN_EPI_GELU = 1, PFN_EPI_GELU_BWD = 2, PFN_EPI_ROWDOT = 3 };
+enum { PFN_EPI_NONE = 0, PFN_EPI_GELU = 1, PFN_EPI_GELU_BWD = 2, PFN_EPI_ROWDOT = 3, PFN_EPI_MUL = 4 };
 enum { PFN_KERNEL_RBF = 0, PFN_KERNEL_MATERN12 = 1, PFN_KERNEL_MATERN32 = 2, PFN_KERNEL_MATERN52 = 3 };
 
 const char* pfn_last_error(void);
@@ -39,6 +39,9 @@ int pfn_num_sms(void);
  *   K-major operand : element (i,k) at base + i*ld + k;   MN-major operand : element (i,k) at base + k*ld + i
  *   epilogue GELU      : C = gelu_erf(acc+bias), optional C2 = acc+bias (pre-activation, saved for backward)
  *   epilogue GELU_BWD  : C = acc * gelu_erf'(aux)
+ *   epilogue MUL       : C = acc * aux   (tcgen05 path only).  With GELU's c2_gelu_grad = 1 the forward stores gelu'(pre)
+ *                        in C2 instead of the pre-activation, and the backward dgrad is this plain product: the ~14
+ *                        instructions per element of gelu' leave the backward epilogue, whose cost is instruction issue.
  *   epilogue ROWDOT    : C = acc (+bias), and rowdot_out[m * ceil(N / rowdot_width) + n / rowdot_width] += sum over the
  *                        column group of C[m,n] * aux[m,n]   (fp32 atomics; aux is NOT added to C).  Used to produce
  *                        delta = rowsum(dO * O) per (token, head) in the out-projection dgrad (tcgen05 path only).
@@ -62,6 +65,7 @@ typedef struct pfn_gemm_desc {
   int ab_dtype;            /* dtype of A, B, aux, C2 (simt path; the tc path is bf16 only) */
   float* rowdot_out;       /* epilogue ROWDOT: [M, ceil(N / rowdot_width)] fp32, accumulated (zero it first) */
   int rowdot_width;        /* columns per group (the head dimension); must be a multiple of 128 */
+  int c2_gelu_grad;        /* epilogue GELU with C2, tcgen05 path only: 1 = C2 receives gelu'(acc+bias) instead of acc+bias */
 } pfn_gemm_desc;
 
 int pfn_gemm_bf16_tc(const pfn_gemm_desc* d, void* stream);

@@ -90,6 +90,17 @@ def test_gemm_tc_epilogues(cuda_device):
     L.gemm(A, B, C, aux=aux, epilogue=L.EPI_GELU_BWD, use_tc=True)
     ref, _ = _ref(A, B, False, False, None, aux, L.EPI_GELU_BWD)
     assert (C.float() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
+    # gelu'(pre) in C2 (forward) + plain product with it (backward): the pair that replaces GELU_BWD on the tcgen05 path
+    L.gemm(A, B, C, bias=bias, C2=C2, epilogue=L.EPI_GELU, c2_gelu_grad=True, use_tc=True)
+    ref, pre = _ref(A, B, False, False, bias, None, L.EPI_GELU)
+    cdf = 0.5 * (1 + torch.erf(pre / 2 ** 0.5))
+    gp = cdf + pre * torch.exp(-0.5 * pre * pre) / (2 * torch.pi) ** 0.5
+    assert (C.float() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
+    assert (C2.float() - gp).abs().max().item() <= 1.5e-2                      # gelu' is O(1); bf16 rounding + approximant
+    L.gemm(A, B, C, aux=C2, epilogue=L.EPI_MUL, use_tc=True)
+    ref, _ = _ref(A, B, False, False, None, None, L.EPI_NONE)
+    ref = ref * C2.float()
+    assert (C.float() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
     # fp32 out
     Cf = torch.empty(M, N, device=cuda_device, dtype=torch.float32)
     L.gemm(A, B, Cf, bias=bias, use_tc=True)

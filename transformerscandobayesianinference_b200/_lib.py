@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PFN_B200_LIB") or os.path.join(_HERE, "libpfn_b200.so")
 
 F32, BF16 = 0, 1
-EPI_NONE, EPI_GELU, EPI_GELU_BWD, EPI_ROWDOT = 0, 1, 2, 3
+EPI_NONE, EPI_GELU, EPI_GELU_BWD, EPI_ROWDOT, EPI_MUL = 0, 1, 2, 3, 4
 KERNEL_RBF, KERNEL_MATERN12, KERNEL_MATERN32, KERNEL_MATERN52 = 0, 1, 2, 3
 
 c_int, c_float, c_void_p = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
@@ -29,7 +29,7 @@ class GemmDesc(ctypes.Structure):
         ("aux", c_void_p), ("ld_aux", c_int),
         ("C2", c_void_p), ("ldc2", c_int),
         ("epilogue", c_int), ("accumulate", c_int), ("k_splits", c_int), ("ab_dtype", c_int),
-        ("rowdot_out", c_void_p), ("rowdot_width", c_int),
+        ("rowdot_out", c_void_p), ("rowdot_width", c_int), ("c2_gelu_grad", c_int),
     ]
 
 
@@ -220,7 +220,7 @@ def _guarded(fn):
 # ------------------------------------------------------------------------------------------------
 @_guarded
 def gemm(A, B, C, *, a_mn_major=False, b_mn_major=False, bias=None, aux=None, C2=None, epilogue=EPI_NONE,
-         accumulate=False, k_splits=1, M=None, N=None, K=None, use_tc=None, rowdot=None):
+         accumulate=False, k_splits=1, M=None, N=None, K=None, use_tc=None, rowdot=None, c2_gelu_grad=False):
     """C[M,N] (+)= epi(A . B^T-ish + bias) (+ aux).  Operands are 2-D row-major tensors (stride(1) == 1)."""
     lib = load()
     require_cuda(A, B, C, bias, aux, C2)
@@ -240,6 +240,7 @@ def gemm(A, B, C, *, a_mn_major=False, b_mn_major=False, bias=None, aux=None, C2
     d.C2, d.ldc2 = (C2.data_ptr(), C2.stride(0)) if C2 is not None else (None, 0)
     d.epilogue, d.accumulate, d.k_splits = epilogue, int(accumulate), k_splits
     d.ab_dtype = dtype_code(A)
+    d.c2_gelu_grad = int(bool(c2_gelu_grad))
     if rowdot is not None:       # (fp32 [M, N // width] zeroed tensor, width): EPI_ROWDOT target
         require_cuda(rowdot[0])
         d.rowdot_out, d.rowdot_width = rowdot[0].data_ptr(), int(rowdot[1])

@@ -144,6 +144,17 @@ __device__ __forceinline__ float gelu_grad_fast(float u) {
   return fmaf(u * hdp, fmaf(-t, t, 1.0f), fmaf(0.5f, t, 0.5f));
 }
 
+// gelu and its derivative from ONE evaluation of the sigmoid: Phi = 1 / (1 + 2^(K u q(u^2))) = sigma(2 p(u)), so
+// d/du [u Phi] = Phi + u * 2 p'(u) * Phi (1 - Phi)   (the same approximant gelu_grad_fast differentiates: 1 - tanh^2 = 4 Phi (1 - Phi))
+__device__ __forceinline__ void gelu_and_grad_fast(float u, float& g, float& gp) {
+  const float u2 = fminf(u * u, 80.0f);
+  const float q = fmaf(u2, fmaf(u2, kGeluC2 * kGeluK, kGeluC1 * kGeluK), kGeluC0 * kGeluK);
+  const float phi = fast_rcp(1.0f + fast_ex2(u * q));
+  const float dp2 = fmaf(u2, fmaf(u2, 10.0f * kGeluC2, 6.0f * kGeluC1), 2.0f * kGeluC0);     // 2 p'(u)
+  g = u * phi;
+  gp = fmaf(u * dp2, fmaf(-phi, phi, phi), phi);
+}
+
 int num_sms();
 
 // Per-device one-time setup guard (function attributes such as the dynamic shared-memory limit are per device).

@@ -50,6 +50,7 @@ struct GemmTcParams {
   int tma_store;                 // 1 => bf16 C (and C2) leave through the smem staging buffer + TMA store
   float* rowdot_out;             // PFN_EPI_ROWDOT: [M, rowdot_groups] fp32, += sum over a column group of C * aux
   int rowdot_width, rowdot_groups;
+  int c2_grad;                   // GELU with C2: C2 = gelu'(pre) instead of pre
 };
 
 constexpr int kBlockM = 128;
@@ -91,7 +92,9 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kDataBytes + 512 + 1024;
 };
 
-template <int BLOCK_N, bool A_MN, bool B_MN, bool CTA2>
+// C2G: the GELU epilogue stores gelu'(pre) in C2 (c2_gelu_grad).  A compile-time switch, instantiated only for the forward
+// linear layout: as a run-time flag its extra live values pushed every instantiation past the register cap (spills).
+template <int BLOCK_N, bool A_MN, bool B_MN, bool CTA2, bool C2G = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const GemmTcParams p) {
@@ -418,7 +421,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           // 16-byte unit (8 bf16) index of this thread's first column inside its 64-column staging chunk
           const int u0 = ((cc & 63) >> 3) + sub * NQ;
-          if (p.act == PFN_EPI_GELU && !write_pre_only) {
+          if (C2G && p.act == PFN_EPI_GELU && write_pre_only) {
+#pragma unroll
+            for (int i = 0; i < kCW; ++i) f[i] = gelu_grad_fast(f[i]);       // two-pass layout: this pass stores C2 = gelu'(pre)
+          }
+          if (C2G && p.act == PFN_EPI_GELU && !write_pre_only) {
+            // C2 = gelu'(pre), C = gelu(pre): eight columns at a time so that only eight derivative values are live
+            if (dual) {
+              uint8_t* rowp = stg + trow * 128;
+#pragma unroll
+              for (int i = 0; i < NQ; ++i) {
+                float gp[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) gelu_and_grad_fast(f[8 * i + e], f[8 * i + e], gp[e]);
+                uint4 pk;
+                pk.x = tc::pack_bf16x2(gp[0], gp[1]); pk.y = tc::pack_bf16x2(gp[2], gp[3]);
+                pk.z = tc::pack_bf16x2(gp[4], gp[5]); pk.w = tc::pack_bf16x2(gp[6], gp[7]);
+                *reinterpret_cast<uint4*>(rowp + (((u0 + i) ^ (trow & 7)) << 4)) = pk;
+              }
+            } else {
+              __nv_bfloat16* dst = p.C2 + static_cast<size_t>(row) * p.ldc2 + col0;
+              const bool direct = p.C2 != nullptr && row_ok && !p.tma_store;      // (two_pass stored C2 in pass 0)
+#pragma unroll
+              for (int i = 0; i < kCW; ++i) {
+                float gp;
+                gelu_and_grad_fast(f[i], f[i], gp);
+                if (direct && col0 + i < p.N) dst[i] = __float2bfloat16_rn(gp);
+              }
+            }
+          } else if (p.act == PFN_EPI_GELU && !write_pre_only) {
             if (dual) {
               // pre-activation goes to chunk slot 0 of the staging buffer (same swizzle as the main output below)
               uint8_t* rowp = stg + trow * 128;
@@ -481,6 +512,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int i = 0; i < kCW; ++i) f[i] *= gelu_grad_fast(a[i]);
 #endif
+            } else if (p.act == PFN_EPI_MUL) {
+#pragma unroll
+              for (int i = 0; i < kCW; ++i) f[i] *= a[i];
             } else if (p.act == PFN_EPI_ROWDOT) {
               // the products use the bf16-ROUNDED outputs (what the consumer of C will read), so that the row sum is
               // exactly the dot product of the stored C with aux
@@ -581,7 +615,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, bool CTA2>
+template <int BLOCK_N, bool A_MN, bool B_MN, bool CTA2, bool C2G = false>
 static int launch_gemm_tc(const pfn_gemm_desc* d, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, CTA2>;
   constexpr int kBRows = CTA2 ? BLOCK_N / 2 : BLOCK_N;   // B rows one CTA loads per stage
@@ -629,6 +663,7 @@ static int launch_gemm_tc(const pfn_gemm_desc* d, cudaStream_t stream) {
   p.C = d->C; p.ldc = d->ldc; p.c_f32 = d->c_dtype == PFN_F32;
   p.C2 = reinterpret_cast<__nv_bfloat16*>(d->C2); p.ldc2 = d->ldc2;
   p.act = d->epilogue;
+  p.c2_grad = d->c2_gelu_grad;
   p.rowdot_out = d->rowdot_out; p.rowdot_width = d->rowdot_width > 0 ? d->rowdot_width : 1;
   p.rowdot_groups = (d->N + p.rowdot_width - 1) / p.rowdot_width;
   constexpr int kTileM = CTA2 ? 2 * kBlockM : kBlockM;
@@ -644,7 +679,7 @@ static int launch_gemm_tc(const pfn_gemm_desc* d, cudaStream_t stream) {
   p.accumulate = (d->accumulate || splits > 1) ? 1 : 0;
   PFN_CHECK_ARG(!p.accumulate || p.c_f32, "gemm_tc: accumulate / split-K requires an fp32 output");
   const int total = p.tiles_m * p.tiles_n * splits;
-  auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN, CTA2>;
+  auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN, CTA2, C2G>;
   static bool attr_set[64] = {};
   if (first_use_on_device(attr_set)) {
     PFN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -680,7 +715,9 @@ extern "C" int pfn_gemm_bf16_tc(const pfn_gemm_desc* d, void* stream) {
   PFN_CHECK_ARG(d->M > 0 && d->N > 0 && d->K > 0, "gemm_tc: empty problem %d x %d x %d", d->M, d->N, d->K);
   PFN_CHECK_ARG(d->lda % 8 == 0 && d->ldb % 8 == 0, "gemm_tc: lda/ldb must be multiples of 8 elements (got %d, %d)",
                 d->lda, d->ldb);
-  PFN_CHECK_ARG(d->epilogue >= 0 && d->epilogue <= PFN_EPI_ROWDOT, "gemm_tc: bad epilogue %d", d->epilogue);
+  PFN_CHECK_ARG(d->epilogue >= 0 && d->epilogue <= PFN_EPI_MUL, "gemm_tc: bad epilogue %d", d->epilogue);
+  PFN_CHECK_ARG(d->epilogue != PFN_EPI_MUL || (d->aux != nullptr && d->k_splits <= 1 && !d->accumulate), "gemm_tc: MUL epilogue needs aux and no split-K");
+  PFN_CHECK_ARG(!d->c2_gelu_grad || (d->epilogue == PFN_EPI_GELU && d->C2 != nullptr), "gemm_tc: c2_gelu_grad needs the GELU epilogue with C2");
   PFN_CHECK_ARG(d->epilogue != PFN_EPI_ROWDOT || (d->aux != nullptr && d->rowdot_out != nullptr && d->rowdot_width >= 128 &&
                                                   d->rowdot_width % 128 == 0 && d->k_splits <= 1 && !d->accumulate),
                 "gemm_tc: ROWDOT epilogue needs aux, rowdot_out, a group width that is a multiple of 128 and no split-K");
@@ -698,6 +735,11 @@ extern "C" int pfn_gemm_bf16_tc(const pfn_gemm_desc* d, void* stream) {
   static int use_pair = -1;
   if (use_pair < 0) { const char* e = getenv("PFN_GEMM_2CTA"); use_pair = (e == nullptr || e[0] != '0') ? 1 : 0; }
   const int key = (wide ? 4 : 0) | (d->a_mn_major ? 2 : 0) | (d->b_mn_major ? 1 : 0);
+  if (d->c2_gelu_grad) {
+    PFN_CHECK_ARG((key & 3) == 0, "gemm_tc: c2_gelu_grad is built for K-major operands (the forward linear layout)");
+    if (wide && use_pair) return launch_gemm_tc<256, false, false, true, true>(d, s);
+    return wide ? launch_gemm_tc<256, false, false, false, true>(d, s) : launch_gemm_tc<128, false, false, false, true>(d, s);
+  }
   if (wide && use_pair) {
     switch (key & 3) {
       case 0: return launch_gemm_tc<256, false, false, true>(d, s);

@@ -460,6 +460,90 @@ layernorm_bwd_ring_kernel(const __nv_bfloat16* __restrict__ dh, int lddh, const 
   }
 }
 
+// bf16 LayerNorm forward with the input rows staged through the same per-warp cp.async ring as the backward.
+template <int NCH>
+__global__ void __launch_bounds__(256, 2)
+layernorm_fwd_ring_kernel(const __nv_bfloat16* __restrict__ z, int ldz, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, __nv_bfloat16* __restrict__ h, int ldh, float* __restrict__ mean_out,
+                          float* __restrict__ rstd_out, int rows, int E, float eps) {
+  extern __shared__ __align__(16) uint8_t ln_smem[];
+  constexpr int ROWB = NCH * 512;
+  const int lane = threadIdx.x & 31;
+  const int warp_in_cta = threadIdx.x >> 5;
+  const int warps_per_cta = blockDim.x >> 5;
+  uint8_t* ring = ln_smem + static_cast<size_t>(warp_in_cta) * LN_RING_D * ROWB;
+  const int warp = blockIdx.x * warps_per_cta + warp_in_cta;
+  const int nwarps = gridDim.x * warps_per_cta;
+  const float inv_e = 1.0f / static_cast<float>(E);
+  float gm[NCH][8], bt[NCH][8];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { gm[c][i] = 0.f; bt[c][i] = 0.f; }
+    const int col = (c * 32 + lane) * 8;
+    if (col < E) { load8<float>(gamma + col, gm[c]); load8<float>(beta + col, bt[c]); }
+  }
+  auto issue = [&](int r, int slot) {
+    if (r < rows) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int col = (c * 32 + lane) * 8;
+        if (col < E) ln_cp_async16(ring + slot * ROWB + (c * 32 + lane) * 16, z + static_cast<size_t>(r) * ldz + col);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+#pragma unroll
+  for (int k = 0; k < LN_RING_D - 1; ++k) issue(warp + k * nwarps, k);
+  int it = 0;
+  for (int row = warp; row < rows; row += nwarps, ++it) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(LN_RING_D - 2) : "memory");
+    __syncwarp();
+    const int slot = it % LN_RING_D;
+    Raw8<__nv_bfloat16> cz[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) cz[c].a = *reinterpret_cast<const uint4*>(ring + slot * ROWB + (c * 32 + lane) * 16);
+    issue(row + (LN_RING_D - 1) * nwarps, (it + LN_RING_D - 1) % LN_RING_D);
+    float v[NCH][8];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int col = (c * 32 + lane) * 8;
+      if (col < E) {
+        unpack8(cz[c], v[c]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += v[c][i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[c][i] = 0.f;
+      }
+    }
+    const float mean = warp_sum(s) * inv_e;
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int col = (c * 32 + lane) * 8;
+      if (col < E) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float dlt = v[c][i] - mean; ss = fmaf(dlt, dlt, ss); }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(ss) * inv_e + eps);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int col = (c * 32 + lane) * 8;
+      if (col < E) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = fmaf((v[c][i] - mean) * rstd, gm[c][i], bt[c][i]);
+        store8<__nv_bfloat16>(h + static_cast<size_t>(row) * ldh + col, o);
+      }
+    }
+    if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 // Generic (any E) fallbacks: one warp per row, scalar accesses, re-reading the row from cache.
 template <typename T>
 __global__ void layernorm_fwd_generic(const T* z, int ldz, const float* gamma, const float* beta, T* h, int ldh,
@@ -630,6 +714,22 @@ static int layernorm_fwd_dispatch(const void* z, int ldz, const float* gamma, co
   int grid = (rows + warps - 1) / warps;
   const int max_grid = num_sms() * 8;
   if (grid > max_grid) grid = max_grid;
+#ifndef PFN_LN_FWD_NO_RING
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    if (vec && E > 256 && E <= 512) {
+      constexpr int NCH = 2;
+      const size_t smem = static_cast<size_t>(warps) * LN_RING_D * NCH * 512;          // 64 KB at depth 8: two CTAs per SM
+      static bool attr_set[64] = {};
+      if (first_use_on_device(attr_set))
+        PFN_CUDA_OK(cudaFuncSetAttribute(layernorm_fwd_ring_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      int g1 = 2 * num_sms();
+      if (g1 > (rows + warps - 1) / warps) g1 = (rows + warps - 1) / warps;
+      layernorm_fwd_ring_kernel<NCH><<<g1, 256, smem, s>>>(zp, ldz, gamma, beta, hp, ldh, mean, rstd, rows, E, eps);
+      PFN_LAUNCH_OK();
+      return 0;
+    }
+  }
+#endif
   if (vec) {
     if (E <= 256) layernorm_fwd_kernel<T, 1><<<grid, 256, 0, s>>>(zp, ldz, gamma, beta, hp, ldh, mean, rstd, rows, E, eps);
     else if (E <= 512) layernorm_fwd_kernel<T, 2><<<grid, 256, 0, s>>>(zp, ldz, gamma, beta, hp, ldh, mean, rstd, rows, E, eps);

@@ -79,6 +79,27 @@ def _linear_fwd(x, w_c, bias, *, aux=None, epilogue=L.EPI_NONE, want_pre=False, 
     return (y, pre) if want_pre else y
 
 
+_GELU_GRAD_FWD = os.environ.get("PFN_B200_GELU_GRAD_FWD", "1") != "0"     # A/B knob (tools/ab_env.sh)
+
+
+def _gelu_linear_fwd(x, w_c, bias):
+    """(gelu(x @ w_c^T + bias), s, s_is_grad): what the backward needs of the GELU is either the pre-activation u
+    (s_is_grad False: the dgrad epilogue evaluates gelu'(u)) or, on the tcgen05 path, gelu'(u) itself, produced by the
+    forward epilogue from the sigmoid it has already computed -- the backward dgrad then only multiplies (the epilogues are
+    bound by instruction issue, and gelu' alone is ~14 instructions per element)."""
+    M, N = x.shape[0], w_c.shape[0]
+    y = torch.empty(M, N, device=x.device, dtype=x.dtype)
+    s = torch.empty(M, N, device=x.device, dtype=x.dtype)
+    as_grad = _GELU_GRAD_FWD and L.tc_gemm_ok(x, w_c, y, None, s)
+    L.gemm(x, w_c, y, bias=bias, C2=s, epilogue=L.EPI_GELU, c2_gelu_grad=as_grad)
+    return y, s, as_grad
+
+
+def _gelu_linear_dgrad(dy, w_c, s, s_is_grad):
+    """dx = (dy @ w_c) * gelu'(u), with s = gelu'(u) (s_is_grad) or s = u."""
+    return _linear_dgrad(dy, w_c, aux=s, epilogue=L.EPI_MUL if s_is_grad else L.EPI_GELU_BWD)
+
+
 def _linear_dgrad(dy, w_c, *, aux=None, epilogue=L.EPI_NONE, rowdot=None):
     """dx = dy @ w_c (+aux | * gelu'(aux) | with rowdot[0][m, k // rowdot[1]] += sum_k dx[m,k] aux[m,k]).
     dy [M,N], w_c [N,K] read as an MN-major B operand."""
@@ -133,7 +154,7 @@ class EncoderStackFn(torch.autograd.Function):
             mean1 = torch.empty(N, device=h.device, dtype=torch.float32)
             rstd1 = torch.empty_like(mean1)
             L.layernorm_fwd(z1, P["g1"], P["be1"], h1, mean1, rstd1, LN_EPS)
-            g, u = _linear_fwd(h1, w1, P["b1"], epilogue=L.EPI_GELU, want_pre=True)
+            g, u, u_is_grad = _gelu_linear_fwd(h1, w1, P["b1"])
             if thr:
                 L.dropout(g, g, site_seed(drop[0], li, 2), thr)                           # dropout(GELU(.)), in place
                 z2 = _linear_fwd(g, w2, P["b2"])
@@ -150,6 +171,7 @@ class EncoderStackFn(torch.autograd.Function):
                 saved.append((h, qkv, attn, lse, z1, mean1, rstd1, h1, u, g, z2, mean2, rstd2, in_w, out_w, w1, w2))
             h = h2
         ctx.saved_acts = saved
+        ctx.u_is_grad = u_is_grad if n_layers else False        # same decision for every layer (same shapes / dtypes)
         ctx.params = params
         ctx.meta = (T, B, sep, nhead, precision, n_layers)
         ctx.drop = drop if thr else None
@@ -189,7 +211,7 @@ class EncoderStackFn(torch.autograd.Function):
                 L.dropout(dz2, dm, site_seed(drop[0], li, 3), drop[1])
                 L.colsum(dm, G["b2"])
             _linear_wgrad(dm, g, G["w2"])
-            du = _linear_dgrad(dm, w2, aux=u, epilogue=L.EPI_GELU_BWD)
+            du = _gelu_linear_dgrad(dm, w2, u, ctx.u_is_grad)
             if drop:
                 L.dropout(du, du, site_seed(drop[0], li, 2), drop[1])       # mask of dropout(GELU(u)) commutes with GELU'(u)
             del g, u, dm
@@ -286,12 +308,13 @@ class DecoderFn(torch.autograd.Function):
         hq = hq.contiguous()
         w0, w2 = _cast(W0, dt), _cast(W2, dt)
         n_out = W2.shape[0]
-        g, u = _linear_fwd(hq, w0, b0, epilogue=L.EPI_GELU, want_pre=True)
+        g, u, u_is_grad = _gelu_linear_fwd(hq, w0, b0)
         ld = (n_out + 3) // 4 * 4
         logits_buf = torch.empty(hq.shape[0], ld, device=hq.device, dtype=torch.float32)
         logits = logits_buf[:, :n_out]
         L.gemm(g, w2, logits, bias=b2.detach().contiguous())
         ctx.save_for_backward(hq, u, g, W0, W2, w0, w2)
+        ctx.u_is_grad = u_is_grad
         ctx.precision = precision
         return logits
 
@@ -313,7 +336,7 @@ class DecoderFn(torch.autograd.Function):
         db2 = flat[sizes[0] + sizes[1] + sizes[2]:]
         L.colsum(dlv, db2)
         _linear_wgrad(dlv, g, dW2)
-        du = _linear_dgrad(dlv, w2, aux=u, epilogue=L.EPI_GELU_BWD)
+        du = _gelu_linear_dgrad(dlv, w2, u, ctx.u_is_grad)
         L.colsum(du, db0)
         _linear_wgrad(du, hq, dW0)
         dhq = _linear_dgrad(du, w0)
