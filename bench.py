@@ -207,7 +207,7 @@ def run_reference(args):
             "config": {"workload": workload_name(args.config, cfg, sample_b), "bounded_sample_batch": sample_b},
             "cpu_baseline": {"value": value, "unit": "seq/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit_line(line)
 
 
 def gpu_eager_baseline(name, cfg, batch, dev, steps=4, warmup=2):
@@ -436,7 +436,16 @@ def run_engine(args):
                        "api": "train.build_trainer -> Trainer.step, batches from priors.<prior>.DataLoader (prefetching)"},
             "clocks": clocks, "gpu_launches": launches, "e2e": e2e,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "gpu_eager_baseline": eager}
-    print(json.dumps(line))
+    emit_line(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit_line(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -452,10 +461,17 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true")
     args = ap.parse_args()
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on fd 1 when
+    # NCCL_DEBUG is set), so fd 1 points at stderr while the run is in progress and the line goes to the saved descriptor.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
         run_engine(args)
+    sys.stdout.flush()
     try:
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized():

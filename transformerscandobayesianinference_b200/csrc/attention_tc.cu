@@ -310,6 +310,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int row = quarter * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     tc::KernelTrace tr = tc::trace_make(p.trace, p.trace_cap, 2);
+    bool s_ok = false;      // early probe result: the next block's scores are already complete
     uint32_t g = 0, tcount = 0;
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
       const int bh = w / p.n_qtiles;
@@ -324,7 +325,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       float m = -INFINITY, l = 0.f;
       for (int j = 0; j < nb; ++j, ++g) {
         const uint32_t buf = g & 1;
-        tc::mbar_wait(&s_full[buf], (g >> 1) & 1);
+        if (!s_ok) tc::mbar_wait(&s_full[buf], (g >> 1) & 1);
         if (threadIdx.x == 64) tr.log(20, w, j);   // S visible to softmax
         tc::tc_fence_after();
         const uint32_t s_tmem = tmem_base + lane_off + buf * ATT_BN;
@@ -432,6 +433,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             pk[2 * q4 + 1] &= m1;
           }
         }
+        // probe of the NEXT block's scores, issued before the P store and consumed at the top of the loop: the ~300-clock
+        // round trip of a probe of an already complete mbarrier then runs under the store instead of in front of the loads
+        s_ok = tc::mbar_try_wait(&s_full[buf ^ 1], ((g + 1) >> 1) & 1);
         tc::tmem_st_32x32b_x32(tmem_base + lane_off + buf * ATT_BN, pk);
         tc::tmem_st_wait();
         tc::tc_fence_before();
@@ -446,19 +450,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const float inv_l = (p.drop_thr > 0 ? drop_scale(p.drop_thr) : 1.0f) / l;     // kept probabilities are scaled by 1 / (1 - p)
       const size_t tokrow = p.batch_major ? static_cast<size_t>(b) * p.T + (valid ? i : 0) : static_cast<size_t>(valid ? i : 0) * p.B + b;
       __nv_bfloat16* orow = p.out + tokrow * p.ld_out + h * ATT_DH;
-#pragma unroll 1
+      // software-pipelined: the TMEM load of chunk c+1 is in flight while chunk c is scaled, packed and stored
+      uint32_t raw[2][32];
+      tc::tmem_ld_32x32b_x32(tmem_base + lane_off + 128, raw[0]);
+#pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t raw[32];
-        tc::tmem_ld_32x32b_x32(tmem_base + lane_off + 128 + c * 32, raw);
         tc::tmem_ld_wait();
+        if (c + 1 < 4) tc::tmem_ld_32x32b_x32(tmem_base + lane_off + 128 + (c + 1) * 32, raw[(c + 1) & 1]);
         if (valid) {
 #pragma unroll
           for (int e = 0; e < 32; e += 8) {
             uint4 pk4;
-            pk4.x = tc::pack_bf16x2(__uint_as_float(raw[e]) * inv_l, __uint_as_float(raw[e + 1]) * inv_l);
-            pk4.y = tc::pack_bf16x2(__uint_as_float(raw[e + 2]) * inv_l, __uint_as_float(raw[e + 3]) * inv_l);
-            pk4.z = tc::pack_bf16x2(__uint_as_float(raw[e + 4]) * inv_l, __uint_as_float(raw[e + 5]) * inv_l);
-            pk4.w = tc::pack_bf16x2(__uint_as_float(raw[e + 6]) * inv_l, __uint_as_float(raw[e + 7]) * inv_l);
+            pk4.x = tc::pack_bf16x2(__uint_as_float(raw[c & 1][e]) * inv_l, __uint_as_float(raw[c & 1][e + 1]) * inv_l);
+            pk4.y = tc::pack_bf16x2(__uint_as_float(raw[c & 1][e + 2]) * inv_l, __uint_as_float(raw[c & 1][e + 3]) * inv_l);
+            pk4.z = tc::pack_bf16x2(__uint_as_float(raw[c & 1][e + 4]) * inv_l, __uint_as_float(raw[c & 1][e + 5]) * inv_l);
+            pk4.w = tc::pack_bf16x2(__uint_as_float(raw[c & 1][e + 6]) * inv_l, __uint_as_float(raw[c & 1][e + 7]) * inv_l);
             *reinterpret_cast<uint4*>(orow + c * 32 + e) = pk4;
           }
         }
