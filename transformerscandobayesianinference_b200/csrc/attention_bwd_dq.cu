@@ -318,7 +318,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
       load_stats(w + gridDim.x, nlse, ndelta, nok);
       if (nd == 0) tc::mbar_arrive_warp(qdo_free);           // no diagonal block: the smem Q / dO tile is already dead
       for (int j = 0; j < nb; ++j) {
-        tc::mbar_wait(&s_full[buf], bphase);
+        tc::mbar_wait_rows(&s_full[buf], bphase);
         if (lane == 0) DQ_LOG(tr, 20 + 100 * warp, tcount, j);
         tc::tc_fence_after();
         const bool diag = j < nd;

@@ -268,7 +268,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gri
         const float stat_next = (i + 1 < nq) ? load_stat(w, i + 1) : load_stat(w + gridDim.x, 0);
         asm volatile("bar.sync 1, 256;" ::: "memory");   // stat[buf] visible; everyone is done reading stat[buf ^ 1]
         if (lane == 0) tr.log(24 + 100 * warp, tcount, i);
-        tc::mbar_wait(st_full, g & 1);
+        tc::mbar_wait_rows(st_full, g & 1);
         if (lane == 0) tr.log(20 + 100 * warp, tcount, i);
         tc::tc_fence_after();
         {

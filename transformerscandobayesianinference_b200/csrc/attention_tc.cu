@@ -325,7 +325,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       float m = -INFINITY, l = 0.f;
       for (int j = 0; j < nb; ++j, ++g) {
         const uint32_t buf = g & 1;
-        if (!s_ok) tc::mbar_wait(&s_full[buf], (g >> 1) & 1);
+        if (!s_ok) tc::mbar_wait_rows(&s_full[buf], (g >> 1) & 1);
         if (threadIdx.x == 64) tr.log(20, w, j);   // S visible to softmax
         tc::tc_fence_after();
         const uint32_t s_tmem = tmem_base + lane_off + buf * ATT_BN;

@@ -122,8 +122,10 @@ __device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
 // Waits of the ROW warps (8-16 warps that all wait for the same barrier at about the same time): with every lane of every
 // warp probing, the probes of one barrier word queue up behind each other; PFN_ROW_POLL_ONE lets lane 0 probe for its warp.
 __device__ __forceinline__ void mbar_wait_rows(uint64_t* bar, uint32_t parity) {
-#ifdef PFN_ROW_POLL_ONE
+#if defined(PFN_ROW_POLL_ONE)
   mbar_wait_warp(bar, parity);
+#elif defined(PFN_ROW_POLL_SLEEP)
+  mbar_wait_backoff<PFN_ROW_POLL_SLEEP>(bar, parity);     // fewer probes per wait (power), up to that many ns of extra latency
 #else
   mbar_wait(bar, parity);
 #endif
