@@ -157,3 +157,16 @@ def test_positional_encoding_and_seqbn_paths(cuda_device):
     out = m((torch.rand(9, 4, 2, device=dev), torch.randn(9, 4, device=dev)), single_eval_pos=4)
     out.square().mean().backward()
     assert m.input_ln.bn.weight.grad is not None
+
+
+def test_explicit_reference_mask_takes_the_same_path(cuda_device):
+    """reference transformer.py:60-65: passing the mask the reference would build itself changes nothing."""
+    m = _small_model(cuda_device, 10).eval()
+    torch.manual_seed(5)
+    x, y = torch.rand(20, 3, 1, device=cuda_device), torch.rand(20, 3, device=cuda_device)
+    with torch.no_grad():
+        a = m((x, y), single_eval_pos=12)
+        b = m((x, y), src_mask=m.generate_D_q_matrix(20, 8).to(cuda_device), single_eval_pos=12)
+        with pytest.raises(NotImplementedError):
+            m((x, y), src_mask=m.generate_square_subsequent_mask(20).to(cuda_device), single_eval_pos=12)
+    assert torch.equal(a, b)

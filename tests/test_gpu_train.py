@@ -192,3 +192,17 @@ def test_explicit_device_argument_and_host_inputs(cuda_device):
                              torch.full((4,), 1e-3).double())
     assert x.shape == (64, 4, 1) and torch.equal(x.transpose(0, 1).cpu(), hx)
     assert (y.transpose(0, 1).cpu().double() - ref).abs().max().item() <= 5e-3 * ref.abs().max().item()
+
+
+def test_cli_main_trains_one_epoch(cuda_device, capsys):
+    """The reference's command line (train.py:151-287) end to end on the GPU at a toy size: parse -> DataLoader -> Trainer ->
+    epochs; returns the reference's `(loss, positional losses, model on cpu)` triple with a finite loss."""
+    torch.manual_seed(0); random.seed(0)
+    loss, pos, model = train_mod.main(
+        ["gp", "--min_y", "-4", "--max_y", "4", "--num_buckets", "20", "--emsize", "64", "--nhead", "2", "--nlayers", "2",
+         "--bptt", "24", "--batch_size", "16", "--steps_per_epoch", "4", "--epochs", "2", "--warmup_epochs", "1",
+         "--pos_encoder", "none", "--lr", "0.001", "--permutation_invariant_max_eval_pos", "20",
+         "--extra_prior_kwargs_dict", "num_features=1"])
+    assert loss == loss and loss < 10 and len(pos) == 24
+    assert next(model.parameters()).device.type == "cpu"
+    assert "ARGS for `train`" in capsys.readouterr().out

@@ -245,3 +245,50 @@ def test_gp_kernel_oracle_known_answers():
     K = O.gp_kernel_ref(x, torch.tensor([[1.0, 2.0]], dtype=torch.float64), one, 0 * one, kernel="rbf")[0]
     assert abs(K[0, 2].item() - math.exp(-0.5)) < 1e-12 and abs(K[1, 2].item() - math.exp(-1.0)) < 1e-12
     assert fast_gp._JITTERS == (0.0, 1e-6, 1e-5, 1e-4)
+
+
+def test_cli_resolves_the_reference_command_line(tmp_path):
+    """`python -m ....train` takes the reference script's arguments (reference train.py:151-287): prior / loss / encoder /
+    positional-encoding names resolve to this package's classes, `nhid` defaults to 2 * emsize, a yaml `--config` overrides
+    defaults and explicit flags override the file."""
+    from transformerscandobayesianinference_b200 import train as train_mod
+    from transformerscandobayesianinference_b200 import priors
+    prior, crit, enc, kw = train_mod.resolve_cli(
+        ["gp", "--min_y", "-3", "--max_y", "3", "--num_buckets", "50", "--emsize", "256", "--bptt", "40",
+         "--extra_prior_kwargs_dict", "num_features=1", "noise=0.1", "--permutation_invariant_max_eval_pos", "30"])
+    assert prior is priors.fast_gp.DataLoader
+    assert isinstance(crit, bar_distribution.BarDistribution) and not isinstance(crit, bar_distribution.FullSupportBarDistribution)
+    assert crit.borders.numel() == 51 and float(crit.borders[0]) == -3.0 and float(crit.borders[-1]) == 3.0
+    assert enc is encoders.Linear and kw["y_encoder_generator"] is encoders.Linear
+    assert kw["pos_encoder_generator"] is positional_encodings.PositionalEncoding
+    assert kw["nhid"] == 512 and kw["emsize"] == 256 and kw["bptt"] == 40 and kw["lr"] == 1e-3 and kw["dropout"] == 0.0
+    assert kw["extra_prior_kwargs_dict"] == {"num_features": 1, "noise": 0.1}
+    assert callable(kw["single_eval_pos_gen"]) and 0 <= kw["single_eval_pos_gen"]() < 30
+    for k in ("prior", "loss_function", "encoder", "pos_encoder", "min_y", "num_buckets", "config"):
+        assert k not in kw                      # everything left is a `train()` keyword
+    import inspect
+    assert set(kw) <= set(inspect.signature(train_mod.train).parameters)
+
+    cfg = tmp_path / "c.yaml"
+    cfg.write_text("epochs: 7\nnlayers: 3\npos_encoder: none\nloss_function: mse\n")
+    prior, crit, enc, kw = train_mod.resolve_cli(["mix_gp", "--config", str(cfg), "--nlayers", "4"])
+    assert prior is priors.fast_gp_mix.DataLoader and isinstance(crit, nn.MSELoss)
+    assert kw["epochs"] == 7 and kw["nlayers"] == 4 and kw["pos_encoder_generator"] is None
+    with pytest.raises(NotImplementedError):
+        train_mod.resolve_cli(["stroke"])
+    with pytest.raises(NotImplementedError):
+        train_mod.resolve_cli(["gp", "--min_y", "0", "--max_y", "1", "--encoder", "mlp"])
+
+
+def test_src_mask_other_than_the_single_eval_pos_mask_is_rejected():
+    """reference transformer.py:60-65: a caller may pass the mask explicitly.  The engine accepts exactly the mask it implements
+    (then proceeds to the device check) and refuses any other pattern."""
+    m = transformer.TransformerModel(nn.Linear(1, 32), 10, 32, 2, 64, 1, 0.0, y_encoder=nn.Linear(1, 32))
+    x, y = torch.zeros(6, 2, 1), torch.zeros(6, 2)
+    good = m.generate_D_q_matrix(6, 2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):          # accepted -> fails later, on the CPU tensors
+        m((x, y), src_mask=good, single_eval_pos=4)
+    with pytest.raises(NotImplementedError):
+        m((x, y), src_mask=m.generate_D_q_matrix(6, 3), single_eval_pos=4)
+    with pytest.raises(NotImplementedError):
+        m((x, y), src_mask=torch.zeros(6, 6), single_eval_pos=4)

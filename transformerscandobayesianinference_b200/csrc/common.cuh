@@ -155,6 +155,76 @@ __device__ __forceinline__ void gelu_and_grad_fast(float u, float& g, float& gp)
   gp = fmaf(u * dp2, fmaf(-phi, phi, phi), phi);
 }
 
+// ---- packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2): one instruction for two elements.  Measured on one B200
+// (tools/ubench/ffma_rate.cu): scalar FFMA 84 FMA/clk/SM, FFMA2 114.  The GELU + GELU' epilogue of a 128 x 256 tile was
+// 482 instructions per 32 elements, 352 of them on the fma pipe -- more pipe clocks than the tile's MMAs take; in pairs it
+// is 307 / 176.  tools/ab_gemm.py, 512000 x 1024 x 512: GELU + gelu' output 0.94 -> 0.80 ms, GELU alone 0.71 -> 0.63 ms.
+// (Pairs in the bias / residual / MUL epilogues measured 2-10 % SLOWER -- they are not instruction-bound -- and stay scalar; a
+// one-MUFU tanh form of the pair GELU measured 0.87 ms: MUFU.TANH is slower than EX2 + RCP here.  Pairs in the softmax / dS
+// arithmetic of the three attention kernels: no change -- 0.94 / 1.25-1.28 / 1.36-1.38 ms either way -- so those stay scalar.)
+#ifndef PFN_EPI_F32X2
+#define PFN_EPI_F32X2 1
+#endif
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack2(float lo, float hi) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ f32x2_t pack2u(uint32_t lo, uint32_t hi) {     // two fp32 bit patterns (e.g. tcgen05.ld words)
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2_t splat2(float c) { return pack2(c, c); }
+__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) {
+  f32x2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// the shared front end of the pair GELUs: u, min(u^2, 80), Phi(u) = 1 / (1 + 2^(K u q(u^2)))
+__device__ __forceinline__ void gelu_phi2(f32x2_t u, f32x2_t& u2, f32x2_t& phi) {
+  float sa, sb;
+  unpack2(mul2(u, u), sa, sb);
+  u2 = pack2(fminf(sa, 80.0f), fminf(sb, 80.0f));
+  const f32x2_t q = fma2(u2, fma2(u2, splat2(kGeluC2 * kGeluK), splat2(kGeluC1 * kGeluK)), splat2(kGeluC0 * kGeluK));
+  float ea, eb;
+  unpack2(mul2(u, q), ea, eb);
+  float da, db;
+  unpack2(add2(pack2(fast_ex2(ea), fast_ex2(eb)), splat2(1.0f)), da, db);
+  phi = pack2(fast_rcp(da), fast_rcp(db));
+}
+// gelu on a pair (same approximant as gelu_fast)
+__device__ __forceinline__ void gelu_fast_pair(float& a, float& b) {
+  const f32x2_t u = pack2(a, b);
+  f32x2_t u2, phi;
+  gelu_phi2(u, u2, phi);
+  unpack2(mul2(u, phi), a, b);
+}
+// gelu and its derivative on a pair (same approximant as gelu_and_grad_fast; the derivative is evaluated as
+// Phi + (2 p'(u) * u Phi) * (1 - Phi), which differs from the scalar form only in the rounding of the last two products)
+__device__ __forceinline__ void gelu_and_grad_fast_pair(float& a, float& b, float& gpa, float& gpb) {
+  const f32x2_t u = pack2(a, b);
+  f32x2_t u2, phi;
+  gelu_phi2(u, u2, phi);
+  const f32x2_t dp2 = fma2(u2, fma2(u2, splat2(10.0f * kGeluC2), splat2(6.0f * kGeluC1)), splat2(2.0f * kGeluC0));   // 2 p'(u)
+  const f32x2_t g = mul2(u, phi);
+  const f32x2_t omp = fma2(phi, splat2(-1.0f), splat2(1.0f));
+  unpack2(fma2(mul2(dp2, g), omp, phi), gpa, gpb);
+  unpack2(g, a, b);
+}
+
 int num_sms();
 
 // Per-device one-time setup guard (function attributes such as the dynamic shared-memory limit are per device).

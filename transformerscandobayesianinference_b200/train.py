@@ -260,3 +260,118 @@ def train(priordataloader_class, criterion, encoder_generator, emsize=200, nhid=
     finally:
         BarDistribution.defer_support_check = prev_defer
     return total_loss, total_positional_losses, model.to('cpu')
+
+
+# ---- command line (reference train.py:137-287) --------------------------------------------------------------
+# `python -m transformerscandobayesianinference_b200.train gp --loss_function barnll --min_y -3 --max_y 3 ...`
+# Same positional / optional arguments, defaults and `--config file.yaml` override as the reference script; the choices the
+# reference names but cannot construct (encoders 'mlp' / 'positional', prior 'stroke') are rejected up front.
+_CLI_PRIORS = {'gp': 'fast_gp', 'mix_gp': 'fast_gp_mix', 'ridge': 'ridge'}
+_CLI_POS_ENCODERS = {'none': None, 'sinus': 'PositionalEncoding', 'learned': 'LearnedPositionalEncoding',
+                     'paired_scrambled_learned': 'PairedScrambledPositionalEncodings'}
+_CLI_SAMPLERS = {'weighted': get_weighted_single_eval_pos_sampler, 'uniform': get_uniform_single_eval_pos_sampler}
+
+
+def _cli_parser():
+    import argparse
+    ap = argparse.ArgumentParser(prog='train', description='Train a PFN on a prior (sm_100a engine).')
+    ap.add_argument('prior', help='gp | mix_gp | ridge')
+    ap.add_argument('--config', help='yaml file whose keys override the defaults below')
+    ap.add_argument('--loss_function', default='barnll',
+                    help='barnll | adaptivebarnll | adaptivefullsupportbarnll | ce | gaussnll | mse')
+    ap.add_argument('--min_y', type=float, help='lower end of the bar distribution support (barnll)')
+    ap.add_argument('--max_y', type=float, help='upper end of the bar distribution support (barnll)')
+    ap.add_argument('--num_buckets', default=100, type=int)
+    ap.add_argument('--extra_prior_kwargs_dict', default={'fuse_x_y': False}, action=StoreDictKeyPair, nargs='+',
+                    metavar='KEY=VAL', help='forwarded to the prior DataLoader')
+    ap.add_argument('--encoder', default='linear')
+    ap.add_argument('--y_encoder', default='linear')
+    ap.add_argument('--pos_encoder', default='sinus', help=' | '.join(_CLI_POS_ENCODERS))
+    ap.add_argument('--bptt', default=10, type=int)
+    ap.add_argument('--epochs', default=200, type=int)
+    ap.add_argument('--warmup_epochs', default=50, type=int)
+    ap.add_argument('--validation_period', default=10, type=int)
+    ap.add_argument('--permutation_invariant_max_eval_pos', default=None, type=int)
+    ap.add_argument('--permutation_invariant_sampling', default='weighted', help='weighted | uniform')
+    ap.add_argument('--emsize', default=512, type=int)
+    ap.add_argument('--nlayers', default=6, type=int)
+    ap.add_argument('--nhid', default=None, type=int, help='default: 2 * emsize')
+    ap.add_argument('--nhead', default=4, type=int)
+    ap.add_argument('--dropout', default=.0, type=float)
+    ap.add_argument('--steps_per_epoch', default=10, type=int)
+    ap.add_argument('--batch_size', default=1000, type=int)
+    ap.add_argument('--lr', '--learning_rate', default=.001, type=float)
+    return ap
+
+
+def resolve_cli(argv=None):
+    """Parse the reference's command line into `(prior DataLoader class, criterion, encoder generator, train kwargs)`."""
+    import importlib
+    ap = _cli_parser()
+    known, _ = ap.parse_known_args(argv)
+    if known.config:
+        import yaml
+        with open(known.config) as f:
+            ap.set_defaults(**yaml.safe_load(f))
+    a = vars(ap.parse_args(argv))
+    a.pop('config')
+    if a['nhid'] is None:
+        a['nhid'] = 2 * a['emsize']
+
+    prior_name = a.pop('prior')
+    if prior_name not in _CLI_PRIORS:
+        raise NotImplementedError(f'Prior == {prior_name}.')
+    prior = importlib.import_module(f'{__package__}.priors.{_CLI_PRIORS[prior_name]}').DataLoader
+
+    def y_sample():
+        dl = prior(num_steps=1, batch_size=a['batch_size'] * a['steps_per_epoch'], seq_len=a['bptt'],
+                   **a['extra_prior_kwargs_dict'])
+        ys = next(iter(dl))[-1]
+        print(f'Creating Bar distribution with borders from y sample of size {ys.numel()}')
+        return ys
+
+    loss, nb, lo, hi = a.pop('loss_function'), a.pop('num_buckets'), a.pop('min_y'), a.pop('max_y')
+    if loss == 'ce':
+        criterion = nn.CrossEntropyLoss(reduction='none')
+    elif loss == 'gaussnll':
+        criterion = nn.GaussianNLLLoss(reduction='none', full=True)
+    elif loss == 'mse':
+        criterion = nn.MSELoss(reduction='none')
+    elif loss == 'barnll':
+        criterion = BarDistribution(borders=get_bucket_limits(nb, full_range=(lo, hi)))
+    elif loss == 'adaptivebarnll':
+        criterion = BarDistribution(borders=get_bucket_limits(nb, ys=y_sample(), full_range=(lo, hi)))
+    elif loss == 'adaptivefullsupportbarnll':
+        assert lo is None and hi is None, 'Please do not specify `min_y` and `max_y` with `adaptivefullsupportbarnll`.'
+        criterion = FullSupportBarDistribution(borders=get_bucket_limits(nb, ys=y_sample()))
+    else:
+        raise NotImplementedError(f'loss_function == {loss}.')
+
+    def encoder_generator(name):
+        if name != 'linear':
+            raise NotImplementedError(f'A {name} encoder is not valid.')
+        return encoders.Linear
+
+    enc, y_enc = encoder_generator(a.pop('encoder')), encoder_generator(a.pop('y_encoder'))
+    pos = a.pop('pos_encoder')
+    if pos not in _CLI_POS_ENCODERS:
+        raise NotImplementedError(f'pos_encoder == {pos} is not valid.')
+    pos_gen = getattr(positional_encodings, _CLI_POS_ENCODERS[pos]) if _CLI_POS_ENCODERS[pos] else None
+
+    max_pos, sampling = a.pop('permutation_invariant_max_eval_pos'), a.pop('permutation_invariant_sampling')
+    if max_pos is not None:
+        if sampling not in _CLI_SAMPLERS:
+            raise ValueError(f'permutation_invariant_sampling == {sampling}')
+        a['single_eval_pos_gen'] = _CLI_SAMPLERS[sampling](max_pos)
+    a.update(y_encoder_generator=y_enc, pos_encoder_generator=pos_gen)
+    return prior, criterion, enc, a
+
+
+def main(argv=None):
+    prior, criterion, enc, kwargs = resolve_cli(argv)
+    print('ARGS for `train`:', kwargs)
+    return train(prior, criterion, enc, **kwargs)
+
+
+if __name__ == '__main__':
+    main()

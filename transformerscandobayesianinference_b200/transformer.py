@@ -77,11 +77,19 @@ class TransformerModel(nn.Module):
     def forward(self, src, src_mask=None, single_eval_pos=None):
         assert single_eval_pos is not None, 'Single eval pos is required now.'
         assert isinstance(src, tuple), 'the fused x/y input mode cannot be combined with single_eval_pos'
-        if src_mask is not None:
-            raise NotImplementedError(
-                "a user-supplied src_mask is not supported by the sm_100a engine: the single_eval_pos mask is "
-                "implicit in the attention kernels (reference transformer.py:60 bypass is out of scope)")
         x_src, y_src = src
+        if src_mask is not None:
+            # The kernels implement exactly the mask the reference builds when none is given (transformer.py:62-65:
+            # generate_D_q_matrix(T, T - single_eval_pos)).  A caller that passes that very mask gets the same fast path; any
+            # other attention pattern is rejected rather than silently replaced.
+            sep_chk = int(single_eval_pos)
+            T_chk = x_src.shape[0]
+            sep_chk = min(max(sep_chk + T_chk, 0) if sep_chk < 0 else sep_chk, T_chk)
+            expect = self.generate_D_q_matrix(T_chk, T_chk - sep_chk).to(src_mask.device)
+            if src_mask.shape != expect.shape or not torch.equal(src_mask.to(expect.dtype), expect):
+                raise NotImplementedError(
+                    "src_mask differs from generate_D_q_matrix(T, T - single_eval_pos): the sm_100a attention kernels "
+                    "implement that mask implicitly and no other (reference transformer.py:60)")
         if not x_src.is_cuda:
             raise RuntimeError(
                 "TransformerModel.forward runs on hand-written sm_100a kernels only; inputs are on "
