@@ -166,3 +166,24 @@ def test_gemm_simt(cuda_device, dtype, M, N, K, a_mn, b_mn):
     L.gemm(A, B, Cf, a_mn_major=a_mn, b_mn_major=b_mn, accumulate=True, k_splits=3, use_tc=False)
     ref, _ = _ref(A, B, a_mn, b_mn, None, None, L.EPI_NONE)
     assert (Cf - (ref + 1)).abs().max().item() <= max(tol, 1e-5) * (ref.abs().max().item() + 1)
+
+
+@pytest.mark.parametrize("M,N,K,b_mn", [(40000, 512, 512, False), (40000, 1024, 256, True), (1000, 200, 256, False),
+                                        (300, 96, 64, False), (129, 328, 128, True)])
+@pytest.mark.parametrize("epi", ["add", "mul"])
+def test_gemm_tc_aux_through_staging(cuda_device, M, N, K, b_mn, epi):
+    """aux tiles (residual / multiplier) reach the epilogue by TMA through the output staging buffer: many tiles per CTA (barrier
+    phases), ragged M and N (zero-filled boxes, clipped stores), padded aux / C leading dimensions, narrow and wide tiles."""
+    torch.manual_seed(M + N)
+    A = _operand(M, K, False, torch.bfloat16, cuda_device)
+    B = (_operand(N, K, b_mn, torch.bfloat16, cuda_device).float() * K ** -0.5).to(torch.bfloat16)
+    ldp = (N + 23) // 8 * 8
+    aux = torch.randn(M, ldp, device=cuda_device).to(torch.bfloat16)[:, :N]
+    C = torch.full((M, ldp + 8), 7.0, device=cuda_device, dtype=torch.bfloat16)[:, :N]
+    bias = torch.randn(N, device=cuda_device) if epi == "add" else None
+    L.gemm(A, B, C, b_mn_major=b_mn, bias=bias, aux=aux, epilogue=L.EPI_NONE if epi == "add" else L.EPI_MUL,
+           M=M, N=N, K=K, use_tc=True)
+    acc = A.float() @ (B.float() if b_mn else B.float().t())
+    ref = acc + bias + aux.float() if epi == "add" else acc * aux.float()
+    assert (C.float() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
+    assert float(C.untyped_storage().nbytes()) > 0 and torch.all(C.as_strided((M, 8), (ldp + 8, 1), N).float() == 7.0)   # padding untouched

@@ -49,6 +49,10 @@ print(" | ".join(out))
 variants = sys.argv[1:] or ["tanh1", "logi1", "tanh2", "logi1nopf"]
 for rnd in range(2):
     for v in variants:
-        env = dict(os.environ, PFN_B200_LIB=os.path.join(HERE, "ubench", "_bin", f"libpfn_{v}.so"))
+        if v.startswith("env:"):       # in-tree library with an environment switch, e.g. env:PFN_GEMM_AUX_TMA=0
+            k, val = v[4:].split("=", 1)
+            env = dict(os.environ, **{k: val})
+        else:
+            env = dict(os.environ, PFN_B200_LIB=os.path.join(HERE, "ubench", "_bin", f"libpfn_{v}.so"))
         r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True, timeout=100)
-        print(f"[{rnd}] {v:10s}: {r.stdout.strip() or r.stderr.strip()[-300:]}", flush=True)
+        print(f"[{rnd}] {v:24s}: {r.stdout.strip() or r.stderr.strip()[-300:]}", flush=True)
