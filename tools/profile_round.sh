@@ -13,7 +13,8 @@ BENCH="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-eager-baselin
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv --log-file gpurun_out/${R}_launches.csv $BENCH > gpurun_out/${R}_ncu_launches.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_ -s 36 -c 4 -f -o gpurun_out/${R}_attn_full $BENCH > gpurun_out/${R}_ncu_attn.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 100 -c 8 -f -o gpurun_out/${R}_gemm_full $BENCH > gpurun_out/${R}_ncu_gemm.log 2>&1
-cuobjdump -sass transformerscandobayesianinference_b200/libpfn_b200.so | grep -oE "UTCHMMA|UTMALDG|UTMASTG|LDTM|STTM|UTCBAR|SYNCS|HMMA|LDGSTS|UBLKCP" | sort | uniq -c > gpurun_out/${R}_sass_mnemonics.txt
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:gp_sample -c 1 -f -o gpurun_out/${R}_gp_full python tools/run_gp_once.py 512 > gpurun_out/${R}_ncu_gp.log 2>&1
+cuobjdump -sass transformerscandobayesianinference_b200/libpfn_b200.so | grep -oE "UTCHMMA|UTMALDG|UTMASTG|LDTM|STTM|UTCBAR|SYNCS|HMMA|LDGSTS|UBLKCP|FFMA2|FMUL2|FADD2" | sort | uniq -c > gpurun_out/${R}_sass_mnemonics.txt
 for f in cfg2 cfg3 cfg4; do echo "== $f: $(python - <<PY
 import json
 try:
