@@ -5,7 +5,7 @@ from transformerscandobayesianinference_b200 import _lib as L
 dev = torch.device("cuda:0")
 N = 512000
 CASES = [(N, 1536, 512, 0, 0, "qkv fwd"), (N, 512, 512, 0, 0, "out fwd"), (N, 512, 1536, 0, 1, "qkv dgrad"), (1536, 512, N, 1, 1, "qkv wgrad"),
-         (N, 1024, 512, 0, 0, "mlp1 plain"), (N, 1024, 512, 0, 0, "mlp1 gelu+c2"), (N, 1024, 512, 0, 1, "mlp2 dgrad gelu'"), (N, 512, 512, 0, 0, "out fwd +aux")]
+         (N, 1024, 512, 0, 0, "mlp1 plain"), (N, 1024, 512, 0, 0, "mlp1 gelu+c2"), (N, 1024, 512, 0, 0, "mlp1 gelu+c2grad"), (N, 1024, 512, 0, 1, "mlp2 dgrad gelu'"), (N, 1024, 512, 0, 1, "mlp2 dgrad mul"), (N, 512, 512, 0, 0, "out fwd +aux")]
 for (M, Nn, K, amn, bmn, name) in CASES:
     A = torch.randn((K, M) if amn else (M, K), device=dev).to(torch.bfloat16)
     Bm = torch.randn((K, Nn) if bmn else (Nn, K), device=dev).to(torch.bfloat16)
@@ -13,7 +13,9 @@ for (M, Nn, K, amn, bmn, name) in CASES:
     C = torch.zeros(M, Nn, device=dev, dtype=torch.float32 if wg else torch.bfloat16)
     kw = {}
     if "gelu+c2" in name:
-        kw = dict(bias=torch.randn(Nn, device=dev), C2=torch.empty_like(C), epilogue=1)
+        kw = dict(bias=torch.randn(Nn, device=dev), C2=torch.empty_like(C), epilogue=1, c2_gelu_grad="grad" in name)
+    elif "mul" in name:
+        kw = dict(aux=torch.randn(M, Nn, device=dev).to(torch.bfloat16), epilogue=4)
     elif "gelu'" in name:
         kw = dict(aux=torch.randn(M, Nn, device=dev).to(torch.bfloat16), epilogue=2)
     elif "+aux" in name:
