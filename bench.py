@@ -204,7 +204,11 @@ def run_reference(args):
             "unit": "seq/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic (prior draws on the host, random-init weights)",
-            "config": {"workload": workload_name(args.config, cfg, sample_b), "bounded_sample_batch": sample_b},
+            # the engine arm's workload (same name, global batch and parallelism keys); each CPU step is a bounded sample of it
+            "config": {"workload": workload_name(args.config, cfg, args.batch or cfg["batch"]),
+                       "global_batch": (args.batch or cfg["batch"]) * max(1, args.gpus), "parallelism": f"dp{max(1, args.gpus)}",
+                       "bounded_sample_batch": sample_b, "precision": "fp32",
+                       "api": "unmodified reference train.train on the host cores (rank 0 only)"},
             "cpu_baseline": {"value": value, "unit": "seq/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit_line(line)
