@@ -7,7 +7,7 @@ OUT=tools/ubench/_bin
 mkdir -p $OUT/obj_$1
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr $2"
 OBJS=""
-for f in runtime optimizer gemm_tc gemm_simt rowwise bar_nll attention_simt attention_tc attention_bwd_tc attention_bwd_dq gp_sampler dropout; do
+for f in runtime optimizer gemm_tc gemm_tc_c2g gemm_simt rowwise bar_nll attention_simt attention_tc attention_bwd_tc attention_bwd_dq gp_sampler dropout; do
   nvcc $FLAGS -c $CS/$f.cu -o $OUT/obj_$1/$f.o &
   OBJS="$OBJS $OUT/obj_$1/$f.o"
 done

@@ -8,7 +8,7 @@ OUT=tools/ubench/_bin
 mkdir -p $OUT/obj
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr"
 VAR=$(basename $1 .cu); shift
-ALL="runtime gemm_tc gemm_simt rowwise bar_nll attention_simt attention_tc attention_bwd_tc attention_bwd_dq gp_sampler dropout optimizer"
+ALL="runtime gemm_tc gemm_tc_c2g gemm_simt rowwise bar_nll attention_simt attention_tc attention_bwd_tc attention_bwd_dq gp_sampler dropout optimizer"
 for f in $ALL; do
   [ $f = $VAR ] && continue
   [ $OUT/obj/$f.o -nt $CS/$f.cu ] || nvcc $FLAGS -c $CS/$f.cu -o $OUT/obj/$f.o &

@@ -20,6 +20,7 @@ SOURCES = [
     "runtime.cu",
     "optimizer.cu",
     "gemm_tc.cu",
+    "gemm_tc_c2g.cu",
     "gemm_simt.cu",
     "rowwise.cu",
     "bar_nll.cu",
@@ -49,6 +50,7 @@ def _nvcc():
 
 def _headers():
     hs = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith((".cuh", ".h"))]
+    hs.append(os.path.join(HERE, "gemm_tc.cu"))          # included by gemm_tc_c2g.cu
     hs.append(os.path.join(ROOT, "include", "pfn_b200.h"))
     return hs
 

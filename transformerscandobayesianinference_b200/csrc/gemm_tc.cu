@@ -721,8 +721,21 @@ static int launch_gemm_tc(const pfn_gemm_desc* d, cudaStream_t stream) {
   return 0;
 }
 
+#ifdef PFN_GEMM_TC_C2G_TU
+// ---- second translation unit (gemm_tc_c2g.cu): ONLY the GELU + gelu' instantiations, built with 16 epilogue warps.  Their
+// epilogue is the critical path of the launch (tools/gemm_stalls.py) and four warps per scheduler hide more of its MUFU /
+// FFMA2 chains (0.84 -> 0.80 ms); every other instantiation stays at 8 warps, where 16 cost 2-3 %.
+int gemm_tc_launch_c2g(const pfn_gemm_desc* d, cudaStream_t s, bool wide, bool use_pair) {
+  if (wide && use_pair) return launch_gemm_tc<256, false, false, true, true>(d, s);
+  return wide ? launch_gemm_tc<256, false, false, false, true>(d, s) : launch_gemm_tc<128, false, false, false, true>(d, s);
+}
+#else
+int gemm_tc_launch_c2g(const pfn_gemm_desc* d, cudaStream_t s, bool wide, bool use_pair);   // gemm_tc_c2g.cu
+#endif
+
 }  // namespace pfn
 
+#ifndef PFN_GEMM_TC_C2G_TU
 extern "C" int pfn_gemm_bf16_tc(const pfn_gemm_desc* d, void* stream) {
   using namespace pfn;
   PFN_CHECK_ARG(d != nullptr, "gemm_tc: null descriptor");
@@ -751,8 +764,7 @@ extern "C" int pfn_gemm_bf16_tc(const pfn_gemm_desc* d, void* stream) {
   const int key = (wide ? 4 : 0) | (d->a_mn_major ? 2 : 0) | (d->b_mn_major ? 1 : 0);
   if (d->c2_gelu_grad) {
     PFN_CHECK_ARG((key & 3) == 0, "gemm_tc: c2_gelu_grad is built for K-major operands (the forward linear layout)");
-    if (wide && use_pair) return launch_gemm_tc<256, false, false, true, true>(d, s);
-    return wide ? launch_gemm_tc<256, false, false, false, true>(d, s) : launch_gemm_tc<128, false, false, false, true>(d, s);
+    return gemm_tc_launch_c2g(d, s, wide, use_pair != 0);
   }
   if (wide && use_pair) {
     switch (key & 3) {
@@ -773,3 +785,4 @@ extern "C" int pfn_gemm_bf16_tc(const pfn_gemm_desc* d, void* stream) {
     default: return launch_gemm_tc<256, true, true, false>(d, s);
   }
 }
+#endif  // !PFN_GEMM_TC_C2G_TU
