@@ -17,7 +17,7 @@ def t(fn, reps=20):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
 out = []
-for (Nn, K, bmn, name) in [(1536, 512, 0, "plain"), (1024, 512, 0, "gelu+c2g"), (1024, 512, 1, "mul"), (1024, 512, 0, "gelu"), (512, 512, 0, "+aux"), (512, 1024, 0, "+aux K1024"), (512, 512, 1, "rowdot")]:
+for (Nn, K, bmn, name) in [(1536, 512, 0, "plain"), (512, 1536, 1, "plain K1536"), (512, 1024, 1, "plain K1024"), (1024, 512, 0, "gelu+c2g"), (1024, 512, 1, "mul"), (1024, 512, 0, "gelu"), (512, 512, 0, "+aux"), (512, 1024, 0, "+aux K1024"), (512, 512, 1, "rowdot")]:
     A = torch.randn(N, K, device=dev).to(torch.bfloat16)
     Bm = (torch.randn((K, Nn) if bmn else (Nn, K), device=dev) * K ** -0.5).to(torch.bfloat16)
     C = torch.zeros(N, Nn, device=dev, dtype=torch.bfloat16)

@@ -51,6 +51,8 @@ struct GemmTcParams {
   float* rowdot_out;             // PFN_EPI_ROWDOT: [M, rowdot_groups] fp32, += sum over a column group of C * aux
   int rowdot_width, rowdot_groups;
   int c2_grad;                   // GELU with C2: C2 = gelu'(pre) instead of pre
+  int stages;                    // operand ring depth of this launch
+  int data_bytes;                // bytes of ring + staging in front of the barriers
 };
 
 constexpr int kBlockM = 128;
@@ -88,8 +90,20 @@ struct GemmCfg {
   static constexpr int kStageOutBytes = kBlockM * BLOCK_N * 2;   // bf16 output tile (two column halves, one per epilogue group)
   static constexpr int kRingBytes = kStagesMax * (kABytes + kBBytes);
   static constexpr int kStagedBytes = kStagesStaged * (kABytes + kBBytes) + kStageOutBytes;
-  static constexpr int kDataBytes = kRingBytes > kStagedBytes ? kRingBytes : kStagedBytes;
-  static constexpr int kSmemBytes = kDataBytes + 512 + 1024;
+  // Plain staged launches (no aux rows to read, one output): one more ring stage out of a 224 KB budget.  Measured on the
+  // 512000 x 1536 x 512 in-projection: 0.746 -> 0.722 ms -- its MMA warp waits for operands, not for the epilogue
+  // (tools/gemm_stalls.py).  Launches that read aux keep the smaller footprint: their rows travel through L1, i.e. through
+  // whatever of the 228 KB is NOT shared memory, and lost 2-4 % under the larger budget.
+  static constexpr int kPlainBudget = 229376;
+  static constexpr int kStagesPlainRaw = (kPlainBudget - kStageOutBytes) / (kABytes + kBBytes);
+  static constexpr int kStagesPlain = kStagesPlainRaw > 6 ? 6 : kStagesPlainRaw;
+  static constexpr int kPlainBytes = kStagesPlain * (kABytes + kBBytes) + kStageOutBytes;
+  static constexpr int kDataBytes = kRingBytes > kStagedBytes ? kRingBytes : kStagedBytes;       // default footprint
+  static constexpr int kDataBytesMax = kPlainBytes > kDataBytes ? kPlainBytes : kDataBytes;
+  static constexpr int kBarrierBytes = 512 + 1024;                                                 // barriers + 1 KB alignment slack
+  static constexpr int kSmemBytes = kDataBytes + kBarrierBytes;
+  static constexpr int kSmemBytesMax = kDataBytesMax + kBarrierBytes;
+  static_assert(kSmemBytesMax <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
 };
 
 // C2G: the GELU epilogue stores gelu'(pre) in C2 (c2_gelu_grad).  A compile-time switch, instantiated only for the forward
@@ -99,7 +113,7 @@ __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const GemmTcParams p) {
   using Cfg = GemmCfg<BLOCK_N, CTA2>;
-  const int STAGES = p.tma_store ? Cfg::kStagesStaged : Cfg::kStagesMax;
+  const int STAGES = p.stages;         // ring depth chosen by the launcher (<= Cfg::kStagesMax barriers exist)
   extern __shared__ uint8_t smem_raw[];
   // 1 KB alignment by an OFFSET on the __shared__ symbol (an integer round trip of the pointer makes every access through it a
   // generic LD.E / ST.E instead of LDS / STS)
@@ -107,7 +121,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * Cfg::kABytes;
   uint8_t* sOut = smem + STAGES * (Cfg::kABytes + Cfg::kBBytes);      // only used when p.tma_store
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kDataBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.data_bytes);
   uint64_t* empty_bar = full_bar + Cfg::kStagesMax;
   uint64_t* tfull_bar = empty_bar + Cfg::kStagesMax;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -678,6 +692,10 @@ static int launch_gemm_tc(const pfn_gemm_desc* d, cudaStream_t stream) {
   p.C2 = reinterpret_cast<__nv_bfloat16*>(d->C2); p.ldc2 = d->ldc2;
   p.act = d->epilogue;
   p.c2_grad = d->c2_gelu_grad;
+  const bool plain = tma_store && d->aux == nullptr && d->C2 == nullptr;
+  p.stages = !tma_store ? Cfg::kStagesMax : (plain ? Cfg::kStagesPlain : Cfg::kStagesStaged);
+  p.data_bytes = plain ? Cfg::kPlainBytes : Cfg::kDataBytes;
+  const int smem_bytes = p.data_bytes + Cfg::kBarrierBytes;
   p.rowdot_out = d->rowdot_out; p.rowdot_width = d->rowdot_width > 0 ? d->rowdot_width : 1;
   p.rowdot_groups = (d->N + p.rowdot_width - 1) / p.rowdot_width;
   constexpr int kTileM = CTA2 ? 2 * kBlockM : kBlockM;
@@ -696,11 +714,11 @@ static int launch_gemm_tc(const pfn_gemm_desc* d, cudaStream_t stream) {
   auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN, CTA2, C2G>;
   static bool attr_set[64] = {};
   if (first_use_on_device(attr_set)) {
-    PFN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    PFN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytesMax));
   }
   if constexpr (!CTA2) {
     const int grid = total < num_sms() ? total : num_sms();
-    kern<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, tmC2, p);
+    kern<<<grid, kNumThreads, smem_bytes, stream>>>(tmA, tmB, tmC, tmC2, p);
   } else {
     const int pairs = num_sms() / 2;
     const int grid = 2 * (total < pairs ? total : pairs);
@@ -708,7 +726,7 @@ static int launch_gemm_tc(const pfn_gemm_desc* d, cudaStream_t stream) {
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kNumThreads);
-    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
