@@ -292,3 +292,28 @@ def test_src_mask_other_than_the_single_eval_pos_mask_is_rejected():
         m((x, y), src_mask=m.generate_D_q_matrix(6, 3), single_eval_pos=4)
     with pytest.raises(NotImplementedError):
         m((x, y), src_mask=torch.zeros(6, 6), single_eval_pos=4)
+
+
+def test_bench_reference_arm_prints_one_json_line_with_the_engine_arms_metric():
+    """The driver divides the engine arm's line by the `--impl reference` line only when both name the same metric / workload:
+    stdout carries exactly ONE JSON line, with the engine arm's METRIC string and workload name (BASELINE.json cfg 2 at batch
+    512/GPU), the bounded CPU sample stated separately, and zero host<->device bytes."""
+    import json, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.exists(os.path.join(root, "oracle", "_ref", "train.py")):
+        pytest.skip("oracle/_ref not built (python -c 'import __graft_entry__ as g; g.build()')")
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--ref-batch", "2"], capture_output=True, text=True, timeout=600, cwd=root,
+                       env=dict(os.environ, PFN_CPU_THREADS="8"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout[:500]
+    d = json.loads(lines[0])
+    sys.path.insert(0, root)
+    import bench
+    assert d["impl"] == "reference" and d["metric"] == bench.METRIC and d["unit"] == "seq/s" and d["higher_is_better"] is True
+    assert d["config"]["workload"] == bench.workload_name("cfg2", bench.CONFIGS["cfg2"], bench.CONFIGS["cfg2"]["batch"])
+    assert d["config"]["global_batch"] == 512 and d["config"]["parallelism"] == "dp1" and d["config"]["bounded_sample_batch"] == 2
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] == 8 and d["cpu_baseline"]["value"] == d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["steps"] == 1 and d["warmup"] == 1 and d["n_gpus"] == 1 and d["vs_baseline"] is None
