@@ -743,12 +743,12 @@ static int launch_gemm_tc(const pfn_gemm_desc* d, cudaStream_t stream) {
 // ---- second translation unit (gemm_tc_c2g.cu): ONLY the GELU + gelu' instantiations, built with 16 epilogue warps.  Their
 // epilogue is the critical path of the launch (tools/gemm_stalls.py) and four warps per scheduler hide more of its MUFU /
 // FFMA2 chains (0.84 -> 0.80 ms); every other instantiation stays at 8 warps, where 16 cost 2-3 %.
-int gemm_tc_launch_c2g(const pfn_gemm_desc* d, cudaStream_t s, bool wide, bool use_pair) {
+__attribute__((visibility("hidden"))) int gemm_tc_launch_c2g(const pfn_gemm_desc* d, cudaStream_t s, bool wide, bool use_pair) {
   if (wide && use_pair) return launch_gemm_tc<256, false, false, true, true>(d, s);
   return wide ? launch_gemm_tc<256, false, false, false, true>(d, s) : launch_gemm_tc<128, false, false, false, true>(d, s);
 }
 #else
-int gemm_tc_launch_c2g(const pfn_gemm_desc* d, cudaStream_t s, bool wide, bool use_pair);   // gemm_tc_c2g.cu
+__attribute__((visibility("hidden"))) int gemm_tc_launch_c2g(const pfn_gemm_desc* d, cudaStream_t s, bool wide, bool use_pair);   // gemm_tc_c2g.cu (library-internal)
 #endif
 
 }  // namespace pfn
