@@ -317,3 +317,80 @@ def test_bench_reference_arm_prints_one_json_line_with_the_engine_arms_metric():
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] == 8 and d["cpu_baseline"]["value"] == d["value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["steps"] == 1 and d["warmup"] == 1 and d["n_gpus"] == 1 and d["vs_baseline"] is None
+
+
+def _load_reference_file(name):
+    """One vendored, unmodified reference module (oracle/_ref/<name>.py) under a private module name."""
+    import importlib.util
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", name + ".py")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref not built (python -c 'import __graft_entry__ as g; g.build()')")
+    spec = importlib.util.spec_from_file_location("_pfn_ref_" + name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_positional_encodings_equal_the_unmodified_reference_modules():
+    """Same seed -> same initial table, same output, same randperm consumption, same state-dict keys, for all four classes
+    (reference positional_encodings.py:13-62)."""
+    ref = _load_reference_file("positional_encodings")
+    x = torch.randn(7, 3, 12)
+    for name in ("NoPositionalEncoding", "PositionalEncoding", "LearnedPositionalEncoding", "PairedScrambledPositionalEncodings"):
+        torch.manual_seed(11); a = getattr(positional_encodings, name)(12, 20)
+        torch.manual_seed(11); b = getattr(ref, name)(12, 20)
+        assert list(a.state_dict()) == list(b.state_dict())
+        for k, v in b.state_dict().items():
+            assert torch.equal(a.state_dict()[k], v), (name, k)
+        a.load_state_dict(b.state_dict(), strict=True)
+        torch.manual_seed(5); ya = a(x)
+        torch.manual_seed(5); yb = b(x)
+        assert torch.equal(ya, yb), name
+        torch.manual_seed(5); a(x); ra = torch.rand(4)
+        torch.manual_seed(5); b(x); rb = torch.rand(4)
+        assert torch.equal(ra, rb), f"{name}: RNG consumption differs"
+    with pytest.raises(AssertionError):
+        positional_encodings.LearnedPositionalEncoding(12, 4)(x)
+    with pytest.raises(AssertionError):
+        positional_encodings.PairedScrambledPositionalEncodings(12, 9)(x)
+
+
+def test_utils_helpers_equal_the_unmodified_reference_module():
+    """SeqBN, set_locals_in_self, StoreDictKeyPair and every step of both schedules against reference utils.py."""
+    import argparse
+    ref = _load_reference_file("utils")
+    for warm, total, cycles in [(0, 10, 0.5), (3, 10, 0.5), (5, 40, 1.5), (10, 10, 0.5)]:
+        for fn, kw in (("get_cosine_schedule_with_warmup", dict(num_cycles=cycles)), ("get_linear_schedule_with_warmup", {})):
+            lrs = []
+            for mod in (utils, ref):
+                opt = torch.optim.SGD([nn.Parameter(torch.zeros(1))], lr=0.7)
+                s = getattr(mod, fn)(opt, warm, total, **kw)
+                cur = []
+                for _ in range(total + 5):
+                    cur.append(s.get_last_lr()[0]); opt.step(); s.step()
+                lrs.append(cur)
+            assert lrs[0] == lrs[1], (fn, warm, total)
+    for n in (1, 2, 37):
+        for fn in ("get_weighted_single_eval_pos_sampler", "get_uniform_single_eval_pos_sampler"):
+            random.seed(n); a = [getattr(utils, fn)(n)() for _ in range(3)] + [f() for f in [getattr(utils, fn)(n)] for _ in range(20)]
+            random.seed(n); b = [getattr(ref, fn)(n)() for _ in range(3)] + [f() for f in [getattr(ref, fn)(n)] for _ in range(20)]
+            assert a == b, (fn, n)
+    torch.manual_seed(0); sa = utils.SeqBN(6)
+    torch.manual_seed(0); sb = ref.SeqBN(6)
+    x = torch.randn(5, 4, 6)
+    assert list(sa.state_dict()) == list(sb.state_dict()) and torch.equal(sa(x), sb(x))
+
+    class Holder:
+        def __init__(self, mod, alpha, beta=3):
+            mod.set_locals_in_self(locals())
+    for mod in (utils, ref):
+        h = Holder(mod, 1.5)
+        assert h.alpha == 1.5 and h.beta == 3 and h.mod is mod and not hasattr(h, "self")
+    out = []
+    for mod in (utils, ref):
+        ap = argparse.ArgumentParser()
+        ap.add_argument("--kw", action=mod.StoreDictKeyPair, nargs="+", default={"d": 1})
+        out.append((ap.parse_args(["--kw", "a=1", "b=2.5", "c=name", "d=[1,2]", "e=None"]).kw, ap.parse_args([]).kw))
+        with pytest.raises(ValueError):
+            ap.parse_args(["--kw", "a=1=2"])
+    assert out[0] == out[1] == ({"a": 1, "b": 2.5, "c": "name", "d": [1, 2], "e": None}, {"d": 1})
